@@ -1,0 +1,244 @@
+// Persistent, warp-specialised tcgen05 GEMM core for sm_100a:   C[m, n] = sum_k A[m, k] * B[n, k]
+// (both operands K-major bf16, fp32 accumulation in tensor memory).  This one mainloop serves the
+// three hot steps: encoder linear layers (A = activations [T, H], B = nn.Linear weight [out, in]),
+// brute-force search (A = queries [nq, d], B = corpus rows [N, d]) and contrastive logits (Q * P^T).
+//
+//   warp 0 (one elected lane)  TMA producer : global -> STAGES-deep smem ring (128B-swizzled boxes)
+//   warp 1 (one elected lane)  MMA issuer   : tcgen05.mma 128 x BN x 16, accumulators in TMEM,
+//                                             double-buffered (2 x BN columns)
+//   warp 2                     TMEM allocator
+//   warps 4..7                 epilogue     : tcgen05.ld -> registers -> Epi functor (fused op)
+//
+// Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue); static persistent
+// tile schedule (tile = blockIdx.x + i * gridDim.x).
+#pragma once
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace om {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+
+template <int BN, int STAGES>
+struct GemmCfg {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
+};
+
+// Epilogue functor contract (all methods __device__, called by the 128 epilogue threads; thread <-> row):
+//   struct State;                                             per-thread, per-tile scratch
+//   void begin(State&, int row, int m_blk, int n_blk) const;  once per tile
+//   void chunk(State&, int row, int col0, const float (&v)[32]) const;   v = C[row, col0 .. col0+31]
+//   void end(State&, int row) const;                           once per tile
+// Rows >= M and columns >= N contain zeros (TMA out-of-bounds fill) and must be masked by the functor.
+
+template <int BN, int STAGES, bool M_FASTEST, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                    int K, Epi epi) {
+  using Cfg = GemmCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = static_cast<int>(threadIdx.x & 31);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int num_m = (M + kBlockM - 1) / kBlockM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
+        const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + k * kUmmaK * 2, kDescKMajorSW128);
+            const uint64_t db = umma_smem_desc(b_addr + k * kUmmaK * 2, kDescKMajorSW128);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
+      const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const int row = m_blk * kBlockM + ew * 32 + lane;
+      typename Epi::State st;
+      epi.begin(st, row, m_blk, n_blk);
+      mbar_wait(&tfull_bar[as], aphase, 4);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        epi.chunk(st, row, n_blk * BN + c * 32, v);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      epi.end(st, row);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Host launcher.  A: [M, K] bf16 row pitch lda elements; B: [N, K] bf16 row pitch ldb elements.
+// Returns cudaSuccess / a CUDA error; tensor-map failures map to cudaErrorInvalidValue.
+template <int BN, int STAGES, bool M_FASTEST, class Epi>
+static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                                      const Epi& epi, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, STAGES>;
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  CUtensorMap tmA, tmB;
+  if (make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBlockK, kBlockM) != 0)
+    return cudaErrorInvalidValue;
+  if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, BN) != 0)
+    return cudaErrorInvalidValue;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, M_FASTEST, Epi>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BN - 1) / BN);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, epi);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------
+// Generic store epilogues
+// --------------------------------------------------------------------------------------------------
+struct EpiStoreF32 {  // C fp32 = acc (+ bias[n]) (+ resid[m, n])
+  float* C;
+  int64_t ldc;
+  const float* bias;   // nullable, [N]
+  const float* resid;  // nullable, [M, ldr]; may alias C
+  int64_t ldr;
+  int M, N;
+  struct State {};
+  __device__ __forceinline__ void begin(State&, int, int, int) const {}
+  __device__ __forceinline__ void end(State&, int) const {}
+  __device__ __forceinline__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
+    if (row >= M || col0 >= N) return;
+    float* out = C + (int64_t)row * ldc + col0;
+    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (bias) {
+          const float4 b = *reinterpret_cast<const float4*>(bias + col0 + i);
+          o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+        }
+        if (resid) {
+          const float4 r = *reinterpret_cast<const float4*>(resid + (int64_t)row * ldr + col0 + i);
+          o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(out + i) = o;
+      }
+    } else {
+      for (int i = 0; i < 32 && col0 + i < N; ++i) {
+        float o = v[i];
+        if (bias) o += bias[col0 + i];
+        if (resid) o += resid[(int64_t)row * ldr + col0 + i];
+        out[i] = o;
+      }
+    }
+  }
+};
+
+}  // namespace om

@@ -1,0 +1,187 @@
+// Standalone bring-up / regression probe for the tcgen05 GEMM core (not part of the shipped library).
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o build/selftest_gemm selftest_gemm.cu
+//   run  : build/selftest_gemm [dump_dir]
+// Exact check: small-integer bf16 operands make every product and partial sum exactly representable
+// in fp32, so the tensor-core result must equal the CPU result bit for bit.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "gemm.cuh"
+
+using namespace om;
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                     \
+    }                                                                              \
+  } while (0)
+
+static uint32_t rng_state = 12345u;
+static inline uint32_t rnd() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return rng_state >> 8;
+}
+
+struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics the search filter)
+  unsigned long long* counter;
+  float thr;
+  int M, N;
+  struct State {
+    int cnt;
+  };
+  __device__ __forceinline__ void begin(State& s, int, int, int) const { s.cnt = 0; }
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s.cnt += (v[i] > thr) ? 1 : 0;
+  }
+  __device__ __forceinline__ void end(State& s, int row) const {
+    if (s.cnt) atomicAdd(counter, (unsigned long long)s.cnt);
+  }
+};
+
+template <int BN, int STAGES, bool MF>
+static int check_case(int M, int N, int K, int num_sms, const char* dump_dir) {
+  printf("[case] BN=%d STAGES=%d M_FASTEST=%d  M=%d N=%d K=%d ... ", BN, STAGES, (int)MF, M, N, K);
+  fflush(stdout);
+  std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
+  std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
+  for (size_t i = 0; i < hA.size(); ++i) {
+    fA[i] = (float)((int)(rnd() % 7) - 3);
+    hA[i] = __float2bfloat16(fA[i]);
+  }
+  for (size_t i = 0; i < hB.size(); ++i) {
+    fB[i] = (float)((int)(rnd() % 7) - 3);
+    hB[i] = __float2bfloat16(fB[i]);
+  }
+  __nv_bfloat16 *dA, *dB;
+  float* dC;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dC, (size_t)M * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
+  EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
+  cudaError_t e = launch_gemm<BN, STAGES, MF>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  if (e != cudaSuccess) {
+    printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("KERNEL FAILED: %s\n", cudaGetErrorString(e));
+    exit(3);
+  }
+  unsigned int fault = read_clear_dev_fault();
+  if (fault) printf("DEVICE FAULT word=0x%08x (site %u, block %u) ", fault, (fault >> 16) & 0x7fff, fault & 0xffff);
+  std::vector<float> hC((size_t)M * N);
+  CK(cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost));
+  size_t bad = 0;
+  double maxerr = 0;
+  int printed = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float ref = 0;
+      for (int k = 0; k < K; ++k) ref += fA[(size_t)m * K + k] * fB[(size_t)n * K + k];
+      float got = hC[(size_t)m * N + n];
+      if (!(got == ref)) {
+        ++bad;
+        double d = fabs((double)got - ref);
+        if (d > maxerr || d != d) maxerr = d;
+        if (printed < 6) {
+          printf("\n   mismatch C[%d,%d] got %g want %g", m, n, got, ref);
+          ++printed;
+        }
+      }
+    }
+  printf("%s  (%zu / %zu mismatches, max |err| %g)\n", bad ? "\n   FAIL" : "ok", bad, hC.size(), maxerr);
+  if (bad && dump_dir) {
+    char path[512];
+    snprintf(path, sizeof path, "%s/gemm_dump_BN%d_M%d_N%d_K%d.bin", dump_dir, BN, M, N, K);
+    FILE* f = fopen(path, "wb");
+    if (f) {
+      int hdr[4] = {M, N, K, BN};
+      fwrite(hdr, 4, 4, f);
+      fwrite(fA.data(), 4, fA.size(), f);
+      fwrite(fB.data(), 4, fB.size(), f);
+      fwrite(hC.data(), 4, hC.size(), f);
+      fclose(f);
+      printf("   dumped operands + result to %s\n", path);
+    }
+  }
+  cudaFree(dA), cudaFree(dB), cudaFree(dC);
+  return bad ? 1 : 0;
+}
+
+template <int BN, int STAGES, bool MF>
+static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters) {
+  __nv_bfloat16 *dA, *dB;
+  unsigned long long* dcnt;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dcnt, 8));
+  CK(cudaMemset(dcnt, 0, 8));
+  // pseudo-random bf16 bit patterns in a sane exponent range: 0x3c00..0x3fff (|x| in [0.0078, 2)) with sign
+  {
+    std::vector<uint16_t> h((size_t)1 << 22);
+    for (auto& x : h) x = (uint16_t)(0x3c00 + (rnd() % 0x400)) | (uint16_t)((rnd() & 1) << 15);
+    for (size_t off = 0; off < (size_t)M * K; off += h.size())
+      CK(cudaMemcpy(dA + off, h.data(), std::min(h.size(), (size_t)M * K - off) * 2, cudaMemcpyHostToDevice));
+    for (size_t off = 0; off < (size_t)N * K; off += h.size())
+      CK(cudaMemcpy(dB + off, h.data(), std::min(h.size(), (size_t)N * K - off) * 2, cudaMemcpyHostToDevice));
+  }
+  EpiCount epi{dcnt, 1.0e30f, M, N};
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm<BN, STAGES, MF>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm<BN, STAGES, MF>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= iters;
+  unsigned int fault = read_clear_dev_fault();
+  double tf = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
+  printf("[perf] %-28s BN=%d ST=%d MF=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", name, BN, STAGES,
+         (int)MF, M, N, K, ms, tf, fault);
+  cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
+}
+
+int main(int argc, char** argv) {
+  const char* dump_dir = argc > 1 ? argv[1] : nullptr;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s  sm_%d%d  SMs=%d  smem/block optin=%zu\n", prop.name, prop.major, prop.minor,
+         prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
+  const int sms = prop.multiProcessorCount;
+  int fails = 0;
+  fails += check_case<256, 4, false>(128, 256, 64, sms, dump_dir);   // one tile, one k-block
+  fails += check_case<256, 4, false>(128, 256, 256, sms, dump_dir);  // one tile, ring wraps once
+  fails += check_case<256, 4, false>(300, 520, 192, sms, dump_dir);  // ragged edges, several tiles
+  fails += check_case<128, 4, false>(300, 520, 192, sms, dump_dir);
+  fails += check_case<64, 4, false>(200, 200, 128, sms, dump_dir);
+  fails += check_case<256, 4, true>(1000, 3000, 768, sms, dump_dir);   // > 1 tile per CTA, both acc buffers
+  fails += check_case<256, 4, false>(2048, 2304, 768, sms, dump_dir);  // many tiles per CTA
+  if (fails) {
+    printf("SELFTEST FAILED (%d cases)\n", fails);
+    return 1;
+  }
+  perf_case<256, 4, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case<256, 4, false>("encoder FFN2 shape", 32768, 768, 3072, sms, 10);
+  perf_case<256, 4, false>("encoder QKV shape", 32768, 2304, 768, sms, 10);
+  perf_case<128, 6, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case<256, 4, true>("search 6980 x 1M", 6980, 1 << 20, 768, sms, 3);
+  perf_case<256, 4, false>("search 6980 x 1M (n fastest)", 6980, 1 << 20, 768, sms, 3);
+  perf_case<256, 4, false>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
+  printf("SELFTEST OK\n");
+  return 0;
+}
