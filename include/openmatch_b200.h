@@ -1,0 +1,138 @@
+/* openmatch_b200 — C ABI of the B200-native dense-retrieval hot path (libopenmatch_b200.so).
+ *
+ * The reference (thunlp/OpenMatch, 100 % Python) has no FFI layer; the seams where its hot path crosses
+ * into third-party compute are three Python call sites, and each entry point below replaces one of them
+ * (paths relative to the reference tree):
+ *
+ *   encoder  : DRModel.encode -> model(**items)          src/openmatch/modeling/dense_retrieval_model.py:133-155
+ *              + mean_pooling                             src/openmatch/utils.py:233-235
+ *              + LinearHead.forward                       src/openmatch/modeling/linear.py:22-23
+ *   index    : faiss.IndexFlatIP(dim) / .add / .search / .reset / .ntotal
+ *                                                         src/openmatch/retriever/dense_retriever.py:38-41,105,133-137,180
+ *              IndexShards merge behind index_cpu_to_gpu_multiple(shard=True)   ...:43-58
+ *   loss     : torch.matmul + cross_entropy (+ autograd)  src/openmatch/loss.py:7-15,
+ *                                                         src/openmatch/modeling/dense_retrieval_model.py:113-125
+ *
+ * Conventions: plain C symbols; every function returns 0 on success and a negative OM_E* code on
+ * failure, om_last_error() then holds a thread-local message.  The caller owns all tensor memory and
+ * passes raw pointers (host or device as stated) plus a CUDA stream handle (cudaStream_t cast to void*,
+ * NULL = legacy default stream); the library owns only its opaque handles.  One process drives one GPU;
+ * a handle is not thread-safe, distinct handles are.  There is no CPU fallback: every compute entry
+ * point fails with OM_ENODEVICE when no sm_100 device is present.
+ */
+#ifndef OPENMATCH_B200_H_
+#define OPENMATCH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OM_ABI_VERSION 1
+
+enum { OM_OK = 0, OM_EINVAL = -1, OM_ECUDA = -2, OM_ENOMEM = -3, OM_ENODEVICE = -4, OM_ESTATE = -5, OM_EFAULT = -6 };
+
+typedef enum { OM_F32 = 0, OM_BF16 = 1, OM_F16 = 2 } om_dtype;
+typedef enum { OM_HOST = 0, OM_DEVICE = 1 } om_memkind;
+typedef enum { OM_ARCH_BERT = 0, OM_ARCH_T5ENC = 1 } om_arch;
+typedef enum { OM_POOL_FIRST = 0, OM_POOL_MEAN = 1 } om_pooling;
+typedef enum { OM_REDUCE_MEAN = 0, OM_REDUCE_SUM = 1 } om_reduction;
+
+typedef struct om_encoder om_encoder;
+typedef struct om_index om_index;
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int om_abi_version(void);
+const char* om_last_error(void);
+/* number of SMs of the current device, or a negative error (OM_ENODEVICE without a GPU) */
+int om_device_sm_count(void);
+
+/* ---- encoder: replaces HF BertModel / T5EncoderModel forward + pooling + head + normalise ---------- */
+typedef struct om_encoder_desc {
+  int32_t arch;             /* om_arch */
+  int32_t layers;           /* num_hidden_layers / num_layers */
+  int32_t hidden;           /* hidden_size / d_model (multiple of 64) */
+  int32_t heads;            /* attention heads; head width is fixed at 64 (bert-base/large, t5-base) */
+  int32_t ffn;              /* intermediate_size / d_ff (multiple of 64) */
+  int32_t vocab;            /* vocab_size */
+  int32_t max_pos;          /* max_position_embeddings (BERT); ignored for T5 */
+  int32_t type_vocab;       /* type_vocab_size (BERT); ignored for T5 */
+  float ln_eps;             /* layer_norm_eps (1e-12 BERT) / layer_norm_epsilon (1e-6 T5) */
+  int32_t pooling;          /* om_pooling: DRModel.pooling 'first' | 'mean' */
+  int32_t has_head;         /* 1: bias-free LinearHead follows pooling */
+  int32_t head_out;         /* LinearHead output_dim (multiple of 8) */
+  int32_t normalize;        /* 1: F.normalize(reps, dim=1) */
+  int32_t rel_buckets;      /* T5 relative_attention_num_buckets (32) */
+  int32_t rel_max_distance; /* T5 relative_attention_max_distance (128) */
+  int32_t max_batch_tokens; /* workspace sizing: max B*L per om_encode call (e.g. 256*128) */
+} om_encoder_desc;
+
+int om_encoder_create(const om_encoder_desc* desc, om_encoder** out);
+/* Parameter by its HuggingFace state_dict name (e.g. "encoder.layer.3.attention.self.query.weight",
+ * "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", or "head.linear.weight" for
+ * the LinearHead).  Data is fp32, row-major, host or device; the library keeps its own packed copy, the
+ * caller's tensor may be freed afterwards.  Unknown names (e.g. "pooler.*", which OpenMatch never uses)
+ * are ignored and reported through the return value 1. */
+int om_encoder_set_weight(om_encoder* enc, const char* name, const void* data, om_memkind kind,
+                          const int64_t* shape, int ndim);
+/* Verifies that every required parameter was supplied and builds derived tables. */
+int om_encoder_finalize(om_encoder* enc);
+/* input_ids / attention_mask / token_type_ids (nullable => zeros; ignored for T5): int64 [B, L] device,
+ * row-major, exactly what DRInferenceCollator / QPCollator hand to the model; L <= 128.
+ * out_reps: device [B, rep_dim] fp32 or bf16 with row pitch out_row_stride (elements) — may point into an
+ * index shard obtained from om_index_reserve().  out_hidden: nullable device fp32 [B, L, hidden]
+ * (last_hidden_state).  Asynchronous on `stream`. */
+int om_encode(om_encoder* enc, const int64_t* input_ids, const int64_t* attention_mask,
+              const int64_t* token_type_ids, int B, int L, void* out_reps, om_dtype out_dtype,
+              int64_t out_row_stride, float* out_hidden, void* stream);
+int om_encoder_rep_dim(const om_encoder* enc);
+void om_encoder_destroy(om_encoder* enc);
+
+/* ---- index: replaces faiss.IndexFlatIP (exact inner-product top-k) -------------------------------- */
+int om_index_create(int d, om_index** out); /* faiss.IndexFlatIP(d); lives on the current device */
+/* index.add(x): x [n, d] row-major, fp32 (host or device).  Rows get ids ntotal .. ntotal+n-1. */
+int om_index_add(om_index* idx, const void* x, om_memkind kind, om_dtype dtype, int64_t n, void* stream);
+/* Zero-copy ingest: reserve room for n more rows and get the device address of the fp32 row block
+ * (row pitch = d floats) so the encoder can write embeddings in place; om_index_commit(n) publishes
+ * them (builds the bf16 scan copy).  */
+int om_index_reserve(om_index* idx, int64_t n, float** dev_rows);
+int om_index_commit(om_index* idx, int64_t n, void* stream);
+int64_t om_index_ntotal(const om_index* idx);
+int om_index_dim(const om_index* idx);
+int om_index_reset(om_index* idx);
+/* D, I = index.search(q, k): q [nq, d] fp32 (host or device); D fp32 [nq, k], I int64 [nq, k] written to
+ * host or device memory (out_kind).  Rows are ordered by (score descending, id ascending); missing
+ * slots (k > ntotal) hold id -1 and score -FLT_MAX, as faiss does.  Reported ids are id_offset + local
+ * row, so a rank of a row-sharded index passes the global id of its first row.  Scores are exact fp32
+ * inner products (candidates are selected on bf16 tensor-core scores with a safety margin, then
+ * re-scored in fp32).  Synchronous with respect to `stream` on return. */
+int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
+                    om_memkind out_kind, int64_t id_offset, void* stream);
+/* Tunables: "rescore_slack" (extra bf16-stage candidates kept per query; default max(64, k/8)),
+ * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing). */
+int om_index_set_param(om_index* idx, const char* name, int64_t value);
+/* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity). */
+int64_t om_index_get_stat(const om_index* idx, const char* name);
+void om_index_destroy(om_index* idx);
+
+/* Exchange step of the row-sharded search: merge `nparts` per-shard results laid out as
+ * D_parts [nparts, nq, k], I_parts [nparts, nq, k] (device) into the global top-k by (score desc, id asc);
+ * ids < 0 are padding.  Matches merge semantics of faiss IndexShards / utils.py:215-229. */
+int om_topk_merge(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k, float* D, int64_t* I,
+                  void* stream);
+
+/* ---- loss: replaces matmul + cross_entropy + autograd backward ------------------------------------ */
+/* Q [nq, d], P [np, d] device, fp32 or bf16 (both the same dtype), row-major.
+ * target: nullable int64 [nq] device (NULL => i * (np / nq), loss.py:11-13).
+ * loss_out: device fp32 scalar = loss_scale * reduce_i(logsumexp_j s_ij - s_i,target_i).
+ * dQ [nq, d], dP [np, d]: nullable device fp32 gradients of loss_out.  scores_out: nullable device fp32
+ * [nq, np] logits (DROutput.scores).  Asynchronous on `stream`. */
+int om_contrastive_loss_fwd_bwd(const void* Q, const void* P, om_dtype dtype, int nq, int np, int d,
+                                const int64_t* target, int reduction, float loss_scale, float* loss_out,
+                                float* dQ, float* dP, float* scores_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENMATCH_B200_H_ */

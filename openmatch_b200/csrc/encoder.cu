@@ -1,0 +1,954 @@
+// B200-native encoder forward behind DRModel.encode (src/openmatch/modeling/dense_retrieval_model.py:133-155):
+// HF BertModel (post-LN, GELU-erf) or T5EncoderModel (pre-RMSNorm, ReLU, shared relative position bias)
+// -> 'first' / 'mean' pooling (:145-150, src/openmatch/utils.py:233-235) -> bias-free LinearHead
+// (src/openmatch/modeling/linear.py:19,22-23) -> F.normalize (:153-154).
+//
+// Per layer (T = B*L tokens, H hidden, I = heads*64 attention width, F ffn):
+//   QKV    tcgen05 GEMM [T,H]x[3I,H]^T, epilogue: +bias -> bf16 Q|K [T,2I] and V transposed [I, T]
+//   ATTN   one CTA per (128-row tile, head): S = Q K^T (tcgen05, TMEM) -> masked softmax in registers
+//          (thread = query row) -> P (bf16, 128B-swizzled smem) -> O = P V (tcgen05) -> ctx bf16 [T,I]
+//   OPROJ  tcgen05 GEMM [T,I]x[H,I]^T, epilogue: +bias +residual -> fp32 residual stream (in place)
+//   NORM   LayerNorm (BERT) / RMSNorm (T5): fp32 statistics, writes fp32 stream + bf16 GEMM operand
+//   FFN1   tcgen05 GEMM [T,H]x[F,H]^T, epilogue: +bias, GELU(erf) / ReLU -> bf16 [T,F]
+//   FFN2   tcgen05 GEMM [T,F]x[H,F]^T, epilogue: +bias +residual -> fp32 stream (in place)
+// Activations feeding tensor cores are bf16; the residual stream, normalisation statistics, softmax,
+// pooling, head and L2-normalisation are fp32.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "gemm.cuh"
+
+namespace om {
+
+constexpr int kHeadDim = 64;
+constexpr int kMaxL = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ===================================================================================================
+// GEMM epilogues
+// ===================================================================================================
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+// out bf16 [M, ldo] = act(acc + bias)
+template <int ACT>
+struct EpiBiasActBf16 {
+  __nv_bfloat16* out;
+  int64_t ldo;
+  const float* bias;  // nullable
+  int M, N;
+  static constexpr int kPasses = 1;
+  struct State {};
+  __device__ __forceinline__ void begin(State&, int, int, int) const {}
+  __device__ __forceinline__ void end(State&, int) const {}
+  __device__ __forceinline__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
+    if (row >= M || col0 >= N) return;  // N is a multiple of 32 for every encoder GEMM (checked on the host)
+    uint32_t packed[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float a = v[i], b = v[i + 1];
+      if (bias) {
+        a += __ldg(bias + col0 + i);
+        b += __ldg(bias + col0 + i + 1);
+      }
+      if (ACT == ACT_GELU) {
+        a = gelu_erf(a);
+        b = gelu_erf(b);
+      } else if (ACT == ACT_RELU) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      packed[i >> 1] = pack_bf16x2(a, b);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+  }
+};
+
+// QKV projection: columns [0, 2I) -> qk bf16 [T, 2I]; columns [2I, 3I) -> vt bf16 [I, ldv] (transposed: the
+// P*V GEMM wants V^T K-major, i.e. token-contiguous)
+struct EpiQKV {
+  __nv_bfloat16* qk;
+  __nv_bfloat16* vt;
+  int64_t ldv;
+  const float* bias;  // nullable, [3I]
+  int M, I2;          // I2 = 2*I
+  static constexpr int kPasses = 1;
+  struct State {};
+  __device__ __forceinline__ void begin(State&, int, int, int) const {}
+  __device__ __forceinline__ void end(State&, int) const {}
+  __device__ __forceinline__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
+    if (row >= M || col0 >= I2 + (I2 >> 1)) return;
+    if (col0 < I2) {
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float a = v[i], b = v[i + 1];
+        if (bias) {
+          a += __ldg(bias + col0 + i);
+          b += __ldg(bias + col0 + i + 1);
+        }
+        packed[i >> 1] = pack_bf16x2(a, b);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(qk + static_cast<int64_t>(row) * I2 + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    } else {
+      __nv_bfloat16* dst = vt + static_cast<int64_t>(col0 - I2) * ldv + row;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float a = v[i];
+        if (bias) a += __ldg(bias + col0 + i);
+        dst[static_cast<int64_t>(i) * ldv] = __float2bfloat16(a);  // lanes = consecutive tokens: coalesced
+      }
+    }
+  }
+};
+
+// ===================================================================================================
+// row-wise kernels: one warp per token row, H % 128 == 0, H <= 1024
+// ===================================================================================================
+constexpr int kMaxVec = 8;  // float4 per lane: 8 * 4 * 32 = 1024 columns
+
+template <bool RMS>
+__device__ __forceinline__ void norm_row(float4 (&v)[kMaxVec], int nvec, int H, float eps) {
+  float s = 0.f;
+  if (!RMS) {
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+      if (j < nvec) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  const float mean = RMS ? 0.f : s / H;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / H + eps);
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) {
+      v[j].x = (v[j].x - mean) * rstd;
+      v[j].y = (v[j].y - mean) * rstd;
+      v[j].z = (v[j].z - mean) * rstd;
+      v[j].w = (v[j].w - mean) * rstd;
+    }
+}
+
+__device__ __forceinline__ void affine_store(const float4 (&v)[kMaxVec], int nvec, int lane, const float* gamma,
+                                             const float* beta, float* out_f32, __nv_bfloat16* out_bf16) {
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) {
+      const int c = (j * 32 + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      float4 y = make_float4(v[j].x * g.x, v[j].y * g.y, v[j].z * g.z, v[j].w * g.w);
+      if (beta) {
+        const float4 b = *reinterpret_cast<const float4*>(beta + c);
+        y.x += b.x, y.y += b.y, y.z += b.z, y.w += b.w;
+      }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + c) = y;
+      if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    }
+}
+
+// y = Norm(h) * gamma (+ beta); writes fp32 (nullable, may alias h) and bf16 (nullable)
+template <bool RMS>
+__global__ void __launch_bounds__(128) norm_kernel(const float* h, const float* gamma, const float* beta, float eps,
+                                                   int T, int H, float* out_f32, __nv_bfloat16* out_bf16) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const int nvec = H >> 7;
+  float4 v[kMaxVec];
+  const float* src = h + static_cast<int64_t>(row) * H;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) v[j] = *reinterpret_cast<const float4*>(src + (j * 32 + lane) * 4);
+  norm_row<RMS>(v, nvec, H, eps);
+  affine_store(v, nvec, lane, gamma, beta, out_f32 ? out_f32 + static_cast<int64_t>(row) * H : nullptr,
+               out_bf16 ? out_bf16 + static_cast<int64_t>(row) * H : nullptr);
+}
+
+// BERT embeddings: LayerNorm(word[id] + type[tt] + pos[l])  (modeling_bert.py:53-112)
+__global__ void __launch_bounds__(128) bert_embed_kernel(const int64_t* ids, const int64_t* tts, const float* word,
+                                                         const float* type, const float* pos, const float* gamma,
+                                                         const float* beta, float eps, int T, int L, int H, int vocab,
+                                                         int type_vocab, float* out_f32, __nv_bfloat16* out_bf16) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const int nvec = H >> 7;
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int64_t tt = tts ? tts[row] : 0;
+  tt = tt < 0 ? 0 : (tt >= type_vocab ? type_vocab - 1 : tt);
+  const int l = row % L;
+  float4 v[kMaxVec];
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) {
+      const int c = (j * 32 + lane) * 4;
+      const float4 a = *reinterpret_cast<const float4*>(word + id * H + c);
+      const float4 b = *reinterpret_cast<const float4*>(type + tt * H + c);
+      const float4 p = *reinterpret_cast<const float4*>(pos + static_cast<int64_t>(l) * H + c);
+      v[j] = make_float4((a.x + b.x) + p.x, (a.y + b.y) + p.y, (a.z + b.z) + p.z, (a.w + b.w) + p.w);
+    }
+  norm_row<false>(v, nvec, H, eps);
+  affine_store(v, nvec, lane, gamma, beta, out_f32 + static_cast<int64_t>(row) * H,
+               out_bf16 + static_cast<int64_t>(row) * H);
+}
+
+// T5: h = embed_tokens[id] (no position embedding, no scaling; modeling_t5.py:682,734)
+__global__ void t5_embed_kernel(const int64_t* ids, const float* emb, int T, int H, int vocab, float* out) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= T) return;
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  for (int c = lane * 4; c < H; c += 128)
+    *reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * H + c) =
+        *reinterpret_cast<const float4*>(emb + id * H + c);
+}
+
+__global__ void keymask_kernel(const int64_t* attn_mask, float* kmask, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) kmask[i] = attn_mask[i] != 0 ? 0.f : __int_as_float(0xff800000);
+}
+
+// ===================================================================================================
+// attention: one CTA per (tile of 128 token rows = spt whole sequences, head)
+// ===================================================================================================
+struct AttnParams {
+  int T, L, spt, I, Tvalid_rows;  // Tvalid_rows = spt * L: rows of the tile that belong to it
+  float scale_log2;               // softmax scale * log2(e)
+  const float* kmask;             // [T] 0 / -inf
+  const float* relbias_log2;      // nullable [heads, 2*kMaxL-1], already multiplied by log2(e)
+  __nv_bfloat16* ctx;             // [T, I]
+};
+
+constexpr int kAttnSmemQ = 0, kAttnSmemK = 16384, kAttnSmemV = 32768, kAttnSmemP = 49152;
+constexpr int kAttnSmemMisc = 49152 + 32768;  // kb[128] f32, rel[256] f32, barriers, tmem slot
+constexpr int kAttnSmemBytes = kAttnSmemMisc + 512 + 1024 + 64 + 1024;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_kb = reinterpret_cast<float*>(smem + kAttnSmemMisc);
+  float* s_rel = s_kb + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rel + 256);  // [0] load, [1] S ready, [2] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x, head = blockIdx.y;
+  const int row0 = tile * p.Tvalid_rows;  // first token of this tile
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmVt);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  {
+    const int tok = row0 + tid;
+    s_kb[tid] = (tid < p.Tvalid_rows && tok < p.T) ? p.kmask[tok] : __int_as_float(0xff800000);
+    if (p.relbias_log2) {
+      for (int i = tid; i < 2 * kMaxL - 1; i += 128) s_rel[i] = p.relbias_log2[head * (2 * kMaxL - 1) + i];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], 3 * 16384);
+    tma_load_2d(smem + kAttnSmemQ, &tmQK, &bars[0], head * kHeadDim, row0);
+    tma_load_2d(smem + kAttnSmemK, &tmQK, &bars[0], p.I + head * kHeadDim, row0);
+    tma_load_2d(smem + kAttnSmemV, &tmVt, &bars[0], row0, head * kHeadDim);
+    tma_load_2d(smem + kAttnSmemV + 8192, &tmVt, &bars[0], row0 + 64, head * kHeadDim);
+    mbar_wait(&bars[0], 0, 10);
+    tc_fence_after_sync();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    const uint32_t qa = smem_u32(smem + kAttnSmemQ), ka = smem_u32(smem + kAttnSmemK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_ss(tmem_base, umma_smem_desc(qa + k * 32, kDescKMajorSW128),
+                   umma_smem_desc(ka + k * 32, kDescKMajorSW128), idesc_s, k != 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0, 11);
+  tc_fence_after_sync();
+
+  // ---- softmax: thread r owns query row r of the tile ----
+  const int r = tid;
+  const bool row_valid = r < p.Tvalid_rows && row0 + r < p.T;
+  const int seq = r / p.L;
+  const int c_lo = row_valid ? seq * p.L : 0, c_hi = row_valid ? c_lo + p.L : 0;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const bool has_rel = p.relbias_log2 != nullptr;
+  float m = __int_as_float(0xff800000);
+#pragma unroll 1
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint32_t raw[32];
+    tmem_ld_32x32b_x32(taddr + c4 * 32, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = c4 * 32 + i;
+      float s = __uint_as_float(raw[i]) * p.scale_log2 + s_kb[c];
+      if (has_rel) s += s_rel[c - r + (kMaxL - 1)];
+      if (c < c_lo || c >= c_hi) s = __int_as_float(0xff800000);
+      m = fmaxf(m, s);
+    }
+  }
+  const bool dead = !(m > __int_as_float(0xff800000));  // every key masked (padding row)
+  const float mm = dead ? 0.f : m;
+  float sum = 0.f;
+  uint8_t* sP = smem + kAttnSmemP;
+#pragma unroll 1
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint32_t raw[32];
+    tmem_ld_32x32b_x32(taddr + c4 * 32, raw);
+    tmem_ld_wait();
+    uint32_t packed[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float pv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c4 * 32 + i + u;
+        float s = __uint_as_float(raw[i + u]) * p.scale_log2 + s_kb[c];
+        if (has_rel) s += s_rel[c - r + (kMaxL - 1)];
+        const bool off = (c < c_lo || c >= c_hi) || dead;
+        pv[u] = off ? 0.f : ex2_approx(s - mm);
+      }
+      sum += pv[0] + pv[1];
+      packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+    }
+    // P[r, c4*32 .. +32) -> K-major SWIZZLE_128B layout: block = c / 64, 16-B chunk j XOR (r & 7)
+    uint8_t* blk = sP + (c4 >> 1) * 16384 + r * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int chunk = ((c4 & 1) * 4 + j) ^ (r & 7);
+      *reinterpret_cast<uint4*>(blk + chunk * 16) =
+          make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+  }
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before_sync();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after_sync();
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+    const uint32_t pa = smem_u32(sP), va = smem_u32(smem + kAttnSmemV);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16_ss(tmem_base + 128, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, kDescKMajorSW128),
+                   umma_smem_desc(va + (k >> 2) * 8192 + (k & 3) * 32, kDescKMajorSW128), idesc_o, k != 0 ? 1u : 0u);
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0, 12);
+  tc_fence_after_sync();
+#pragma unroll 1
+  for (int c2 = 0; c2 < 2; ++c2) {
+    uint32_t raw[32];
+    tmem_ld_32x32b_x32(taddr + 128 + c2 * 32, raw);
+    tmem_ld_wait();
+    if (row_valid) {
+      uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<int64_t>(row0 + r) * p.I + head * kHeadDim + c2 * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          w[u] = pack_bf16x2(__uint_as_float(raw[8 * j + 2 * u]) * inv, __uint_as_float(raw[8 * j + 2 * u + 1]) * inv);
+        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ===================================================================================================
+// pooling / head / normalise (fp32)
+// ===================================================================================================
+// pooled[b, :] = hidden[b, 0, :]  or  sum_l hidden[b,l,:] m[b,l] / clamp(sum_l m[b,l], 1e-9)
+__global__ void pool_kernel(const float* hidden, const int64_t* mask, int L, int H, int mean, float* pooled) {
+  const int b = blockIdx.x;
+  const float* src = hidden + static_cast<int64_t>(b) * L * H;
+  if (!mean) {
+    for (int c = threadIdx.x; c < H; c += blockDim.x) pooled[static_cast<int64_t>(b) * H + c] = src[c];
+    return;
+  }
+  __shared__ float sm[kMaxL];
+  for (int l = threadIdx.x; l < L; l += blockDim.x) sm[l] = mask[static_cast<int64_t>(b) * L + l] != 0 ? 1.f : 0.f;
+  __syncthreads();
+  float cnt = 0.f;
+  for (int l = 0; l < L; ++l) cnt += sm[l];
+  const float denom = fmaxf(cnt, 1e-9f);
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) acc += src[static_cast<int64_t>(l) * H + c] * sm[l];
+    pooled[static_cast<int64_t>(b) * H + c] = acc / denom;
+  }
+}
+
+// out[b, o] = sum_i in[b, i] * W[o, i]  (bias-free LinearHead).  One warp per (o, group of 8 rows).
+__global__ void __launch_bounds__(256) head_kernel(const float* in, const float* W, int B, int Hin, int Hout, float* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int groups = (B + 7) / 8;
+  if (warp >= Hout * groups) return;
+  const int o = warp % Hout, g = warp / Hout;
+  const float* w = W + static_cast<int64_t>(o) * Hin;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = lane; i < Hin; i += 32) {
+    const float wv = __ldg(w + i);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = g * 8 + u;
+      if (b < B) acc[u] = fmaf(in[static_cast<int64_t>(b) * Hin + i], wv, acc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], s);
+    const int b = g * 8 + u;
+    if (lane == 0 && b < B) out[static_cast<int64_t>(b) * Hout + o] = acc[u];
+  }
+}
+
+// F.normalize(x, dim=1) = x / max(||x||_2, 1e-12) (optional) and store as fp32 / bf16 with a row pitch
+template <typename OutT>
+__global__ void finish_reps_kernel(const float* in, int B, int D, int normalize, OutT* out, int64_t pitch) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* src = in + static_cast<int64_t>(b) * D;
+  float scale = 1.f;
+  if (normalize) {
+    float q = 0.f;
+    for (int i = lane; i < D; i += 32) q = fmaf(src[i], src[i], q);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) q += __shfl_xor_sync(0xffffffffu, q, s);
+    scale = 1.0f / fmaxf(sqrtf(q), 1e-12f);
+  }
+  for (int i = lane; i < D; i += 32) out[static_cast<int64_t>(b) * pitch + i] = static_cast<OutT>(src[i] * scale);
+}
+
+__global__ void f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+// T5 relative-position bucket (bidirectional), same fp32 arithmetic as modeling_t5.py:188-234
+static int t5_bucket(int rel, int num_buckets, int max_distance) {
+  const int nb = num_buckets / 2;
+  const int out = rel > 0 ? nb : 0;
+  const int n = rel < 0 ? -rel : rel;
+  const int max_exact = nb / 2;
+  if (n < max_exact) return out + n;
+  const float v = logf(static_cast<float>(n) / static_cast<float>(max_exact)) /
+                  static_cast<float>(log(static_cast<double>(max_distance) / static_cast<double>(max_exact))) *
+                  static_cast<float>(nb - max_exact);
+  int large = max_exact + static_cast<int>(v);
+  if (large > nb - 1) large = nb - 1;
+  return out + large;
+}
+
+}  // namespace om
+
+using namespace om;
+
+// ===================================================================================================
+// host side
+// ===================================================================================================
+struct LayerW {
+  __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;  // [3I,H] [H,I] [F,H] [H,F]
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;          // BERT only
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;  // BERT: post-attn / post-ffn LN
+                                                                                 // T5  : pre-attn / pre-ffn RMS (g only)
+};
+
+struct om_encoder {
+  om_encoder_desc d;
+  int I = 0;  // heads * 64
+  std::vector<LayerW> layers;
+  float *word = nullptr, *pos = nullptr, *type = nullptr, *emb_g = nullptr, *emb_b = nullptr;  // BERT embeddings
+  float* final_g = nullptr;                                                                    // T5 final RMSNorm
+  float* rel_w = nullptr;         // T5 [buckets, heads] (host copy kept in rel_host)
+  std::vector<float> rel_host;
+  float* relbias_log2 = nullptr;  // [heads, 255]
+  float* head_w = nullptr;        // [head_out, H]
+  std::vector<std::string> missing;
+  std::vector<std::pair<std::string, bool>> required;  // name -> set?
+  bool finalized = false;
+  // workspace
+  int Tmax = 0, Tld = 0;
+  float *h = nullptr, *kmask = nullptr, *pooled = nullptr, *headed = nullptr;
+  __nv_bfloat16 *xb = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *inter = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(om_encoder* e, T** p, size_t count) {
+  void* q = nullptr;
+  OM_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  e->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+void require(om_encoder* e, const std::string& name) { e->required.emplace_back(name, false); }
+
+int mark(om_encoder* e, const std::string& name) {
+  for (auto& r : e->required)
+    if (r.first == name) {
+      r.second = true;
+      return 0;
+    }
+  return 1;
+}
+
+// copies a fp32 [rows, cols] block (host or device) into dst (+ optional bf16 conversion)
+int upload(const void* data, om_memkind kind, size_t count, float* dst_f32, __nv_bfloat16* dst_bf16) {
+  float* staged = dst_f32;
+  float* tmp = nullptr;
+  if (!staged) {
+    OM_CUDA(cudaMalloc(&tmp, count * sizeof(float)));
+    staged = tmp;
+  }
+  cudaError_t err =
+      cudaMemcpy(staged, data, count * sizeof(float), kind == OM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice);
+  if (err == cudaSuccess && dst_bf16) {
+    f32_to_bf16_kernel<<<static_cast<int>(std::min<size_t>((count + 255) / 256, 4096)), 256>>>(staged, dst_bf16,
+                                                                                              (int64_t)count);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  }
+  if (tmp) cudaFree(tmp);
+  if (err != cudaSuccess) return fail(OM_ECUDA, "weight upload failed: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+bool shape_is(const int64_t* shape, int ndim, int64_t a, int64_t b = -1) {
+  if (b < 0) return ndim == 1 && shape[0] == a;
+  return ndim == 2 && shape[0] == a && shape[1] == b;
+}
+
+int bad_shape(const char* name) { return fail(OM_EINVAL, "om_encoder_set_weight: unexpected shape for '%s'", name); }
+
+}  // namespace
+
+extern "C" {
+
+int om_encoder_create(const om_encoder_desc* desc, om_encoder** out) {
+  if (!desc || !out) return fail(OM_EINVAL, "om_encoder_create: null argument");
+  OM_TRY(device_sm_count());
+  const om_encoder_desc& d = *desc;
+  if (d.arch != OM_ARCH_BERT && d.arch != OM_ARCH_T5ENC) return fail(OM_EINVAL, "unknown arch %d", d.arch);
+  if (d.hidden <= 0 || d.hidden % 128 != 0 || d.hidden > 1024)
+    return fail(OM_EINVAL, "hidden=%d unsupported (multiple of 128, <= 1024)", d.hidden);
+  if (d.heads <= 0 || d.heads * kHeadDim > 2048 || (d.heads * kHeadDim) % 128 != 0)
+    return fail(OM_EINVAL, "heads=%d unsupported (head width is 64; heads*64 must be a multiple of 128)", d.heads);
+  if (d.arch == OM_ARCH_BERT && d.heads * kHeadDim != d.hidden)
+    return fail(OM_EINVAL, "BERT requires hidden == heads * 64 (got hidden=%d heads=%d)", d.hidden, d.heads);
+  if (d.ffn <= 0 || d.ffn % 64 != 0) return fail(OM_EINVAL, "ffn=%d must be a positive multiple of 64", d.ffn);
+  if (d.layers <= 0 || d.vocab <= 0) return fail(OM_EINVAL, "layers/vocab must be positive");
+  if (d.has_head && (d.head_out <= 0)) return fail(OM_EINVAL, "head_out must be positive when has_head=1");
+  if (d.max_batch_tokens <= 0) return fail(OM_EINVAL, "max_batch_tokens must be positive");
+  om_encoder* e = new (std::nothrow) om_encoder();
+  if (!e) return fail(OM_ENOMEM, "out of host memory");
+  e->d = d;
+  e->I = d.heads * kHeadDim;
+  const int H = d.hidden, I = e->I, F = d.ffn;
+  e->layers.resize(d.layers);
+  int rc = 0;
+  auto A = [&](auto** p, size_t n) {
+    if (rc == 0) rc = dev_alloc(e, p, n);
+  };
+  if (d.arch == OM_ARCH_BERT) {
+    A(&e->word, (size_t)d.vocab * H);
+    A(&e->pos, (size_t)d.max_pos * H);
+    A(&e->type, (size_t)std::max(d.type_vocab, 1) * H);
+    A(&e->emb_g, H);
+    A(&e->emb_b, H);
+    require(e, "embeddings.word_embeddings.weight");
+    require(e, "embeddings.position_embeddings.weight");
+    require(e, "embeddings.token_type_embeddings.weight");
+    require(e, "embeddings.LayerNorm.weight");
+    require(e, "embeddings.LayerNorm.bias");
+  } else {
+    A(&e->word, (size_t)d.vocab * H);
+    A(&e->final_g, H);
+    A(&e->rel_w, (size_t)d.rel_buckets * d.heads);
+    A(&e->relbias_log2, (size_t)d.heads * (2 * kMaxL - 1));
+    require(e, "shared.weight");
+    require(e, "encoder.final_layer_norm.weight");
+    require(e, "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight");
+  }
+  for (int i = 0; i < d.layers; ++i) {
+    LayerW& w = e->layers[i];
+    A(&w.wqkv, (size_t)3 * I * H);
+    A(&w.wo, (size_t)H * I);
+    A(&w.w1, (size_t)F * H);
+    A(&w.w2, (size_t)H * F);
+    A(&w.ln1_g, H);
+    A(&w.ln2_g, H);
+    char buf[160];
+    if (d.arch == OM_ARCH_BERT) {
+      A(&w.bqkv, (size_t)3 * I);
+      A(&w.bo, H);
+      A(&w.b1, F);
+      A(&w.b2, H);
+      A(&w.ln1_b, H);
+      A(&w.ln2_b, H);
+      static const char* names[] = {"attention.self.query", "attention.self.key", "attention.self.value",
+                                    "attention.output.dense", "attention.output.LayerNorm", "intermediate.dense",
+                                    "output.dense", "output.LayerNorm"};
+      for (const char* n : names)
+        for (const char* suffix : {"weight", "bias"}) {
+          snprintf(buf, sizeof buf, "encoder.layer.%d.%s.%s", i, n, suffix);
+          require(e, buf);
+        }
+    } else {
+      static const char* names[] = {"layer.0.SelfAttention.q", "layer.0.SelfAttention.k", "layer.0.SelfAttention.v",
+                                    "layer.0.SelfAttention.o", "layer.0.layer_norm", "layer.1.DenseReluDense.wi",
+                                    "layer.1.DenseReluDense.wo", "layer.1.layer_norm"};
+      for (const char* n : names) {
+        snprintf(buf, sizeof buf, "encoder.block.%d.%s.weight", i, n);
+        require(e, buf);
+      }
+    }
+  }
+  if (d.has_head) {
+    A(&e->head_w, (size_t)d.head_out * H);
+    require(e, "head.linear.weight");
+  }
+  // workspace
+  e->Tmax = d.max_batch_tokens;
+  e->Tld = static_cast<int>(round_up(e->Tmax, 8));
+  const size_t T = e->Tmax;
+  A(&e->h, T * H);
+  A(&e->kmask, T);
+  A(&e->xb, T * H);
+  A(&e->qk, T * 2 * I);
+  A(&e->vt, (size_t)I * e->Tld);
+  A(&e->ctx, T * I);
+  A(&e->inter, T * F);
+  A(&e->pooled, T * H);  // at most Tmax sequences (L >= 1)
+  A(&e->headed, (size_t)e->Tmax * std::max(d.head_out, 1));
+  if (rc != 0) {
+    om_encoder_destroy(e);
+    return rc;
+  }
+  if (cudaMemset(e->vt, 0, (size_t)I * e->Tld * 2) != cudaSuccess) {
+    om_encoder_destroy(e);
+    return fail(OM_ECUDA, "workspace memset failed");
+  }
+  *out = e;
+  return 0;
+}
+
+void om_encoder_destroy(om_encoder* e) {
+  if (!e) return;
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+int om_encoder_rep_dim(const om_encoder* e) { return e ? (e->d.has_head ? e->d.head_out : e->d.hidden) : 0; }
+
+int om_encoder_set_weight(om_encoder* e, const char* name_c, const void* data, om_memkind kind, const int64_t* shape,
+                          int ndim) {
+  if (!e || !name_c || !data || !shape) return fail(OM_EINVAL, "om_encoder_set_weight: null argument");
+  std::string name(name_c);
+  if (name.rfind("bert.", 0) == 0) name = name.substr(5);  // BertFor* checkpoints prefix the backbone
+  const om_encoder_desc& d = e->d;
+  const int H = d.hidden, I = e->I, F = d.ffn;
+  e->finalized = false;
+  if (name == "encoder.embed_tokens.weight") name = "shared.weight";
+  if (name == "head.linear.weight" || name == "linear.weight") {
+    if (!d.has_head) return 1;
+    if (!shape_is(shape, ndim, d.head_out, H)) return bad_shape(name_c);
+    OM_TRY(upload(data, kind, (size_t)d.head_out * H, e->head_w, nullptr));
+    mark(e, "head.linear.weight");
+    return 0;
+  }
+  if (d.arch == OM_ARCH_BERT) {
+    if (name == "embeddings.word_embeddings.weight") {
+      if (!shape_is(shape, ndim, d.vocab, H)) return bad_shape(name_c);
+      OM_TRY(upload(data, kind, (size_t)d.vocab * H, e->word, nullptr));
+    } else if (name == "embeddings.position_embeddings.weight") {
+      if (!shape_is(shape, ndim, d.max_pos, H)) return bad_shape(name_c);
+      OM_TRY(upload(data, kind, (size_t)d.max_pos * H, e->pos, nullptr));
+    } else if (name == "embeddings.token_type_embeddings.weight") {
+      if (!shape_is(shape, ndim, d.type_vocab, H)) return bad_shape(name_c);
+      OM_TRY(upload(data, kind, (size_t)d.type_vocab * H, e->type, nullptr));
+    } else if (name == "embeddings.LayerNorm.weight" || name == "embeddings.LayerNorm.bias") {
+      if (!shape_is(shape, ndim, H)) return bad_shape(name_c);
+      OM_TRY(upload(data, kind, H, name.back() == 't' ? e->emb_g : e->emb_b, nullptr));
+    } else if (name.rfind("encoder.layer.", 0) == 0) {
+      int li = -1, consumed = 0;
+      if (sscanf(name.c_str(), "encoder.layer.%d.%n", &li, &consumed) != 1 || li < 0 || li >= d.layers) return 1;
+      const std::string rest = name.substr(consumed);
+      LayerW& w = e->layers[li];
+      const bool is_w = rest.size() > 7 && rest.compare(rest.size() - 7, 7, ".weight") == 0;
+      const std::string mod = rest.substr(0, rest.rfind('.'));
+      int slot = mod == "attention.self.query" ? 0 : mod == "attention.self.key" ? 1 : mod == "attention.self.value" ? 2 : -1;
+      if (slot >= 0) {
+        if (is_w) {
+          if (!shape_is(shape, ndim, I, H)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, (size_t)I * H, nullptr, w.wqkv + (size_t)slot * I * H));
+        } else {
+          if (!shape_is(shape, ndim, I)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, I, w.bqkv + (size_t)slot * I, nullptr));
+        }
+      } else if (mod == "attention.output.dense") {
+        if (is_w) {
+          if (!shape_is(shape, ndim, H, I)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, (size_t)H * I, nullptr, w.wo));
+        } else {
+          if (!shape_is(shape, ndim, H)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, H, w.bo, nullptr));
+        }
+      } else if (mod == "attention.output.LayerNorm" || mod == "output.LayerNorm") {
+        if (!shape_is(shape, ndim, H)) return bad_shape(name_c);
+        float* dst = mod[0] == 'a' ? (is_w ? w.ln1_g : w.ln1_b) : (is_w ? w.ln2_g : w.ln2_b);
+        OM_TRY(upload(data, kind, H, dst, nullptr));
+      } else if (mod == "intermediate.dense") {
+        if (is_w) {
+          if (!shape_is(shape, ndim, F, H)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, (size_t)F * H, nullptr, w.w1));
+        } else {
+          if (!shape_is(shape, ndim, F)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, F, w.b1, nullptr));
+        }
+      } else if (mod == "output.dense") {
+        if (is_w) {
+          if (!shape_is(shape, ndim, H, F)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, (size_t)H * F, nullptr, w.w2));
+        } else {
+          if (!shape_is(shape, ndim, H)) return bad_shape(name_c);
+          OM_TRY(upload(data, kind, H, w.b2, nullptr));
+        }
+      } else {
+        return 1;
+      }
+    } else {
+      return 1;  // e.g. pooler.*: computed by HF, never used by OpenMatch
+    }
+  } else {
+    if (name == "shared.weight") {
+      if (!shape_is(shape, ndim, d.vocab, H)) return bad_shape(name_c);
+      OM_TRY(upload(data, kind, (size_t)d.vocab * H, e->word, nullptr));
+    } else if (name == "encoder.final_layer_norm.weight") {
+      if (!shape_is(shape, ndim, H)) return bad_shape(name_c);
+      OM_TRY(upload(data, kind, H, e->final_g, nullptr));
+    } else if (name.rfind("encoder.block.", 0) == 0) {
+      int li = -1, consumed = 0;
+      if (sscanf(name.c_str(), "encoder.block.%d.%n", &li, &consumed) != 1 || li < 0 || li >= d.layers) return 1;
+      const std::string rest = name.substr(consumed);
+      LayerW& w = e->layers[li];
+      if (rest == "layer.0.SelfAttention.relative_attention_bias.weight") {
+        if (li != 0) return 1;
+        if (!shape_is(shape, ndim, d.rel_buckets, d.heads)) return bad_shape(name_c);
+        OM_TRY(upload(data, kind, (size_t)d.rel_buckets * d.heads, e->rel_w, nullptr));
+        e->rel_host.resize((size_t)d.rel_buckets * d.heads);
+        OM_CUDA(cudaMemcpy(e->rel_host.data(), e->rel_w, e->rel_host.size() * 4, cudaMemcpyDeviceToHost));
+      } else if (rest == "layer.0.SelfAttention.q.weight" || rest == "layer.0.SelfAttention.k.weight" ||
+                 rest == "layer.0.SelfAttention.v.weight") {
+        const int slot = rest[22] == 'q' ? 0 : rest[22] == 'k' ? 1 : 2;
+        if (!shape_is(shape, ndim, I, H)) return bad_shape(name_c);
+        OM_TRY(upload(data, kind, (size_t)I * H, nullptr, w.wqkv + (size_t)slot * I * H));
+      } else if (rest == "layer.0.SelfAttention.o.weight") {
+        if (!shape_is(shape, ndim, H, I)) return bad_shape(name_c);
+        OM_TRY(upload(data, kind, (size_t)H * I, nullptr, w.wo));
+      } else if (rest == "layer.0.layer_norm.weight" || rest == "layer.1.layer_norm.weight") {
+        if (!shape_is(shape, ndim, H)) return bad_shape(name_c);
+        OM_TRY(upload(data, kind, H, rest[6] == '0' ? w.ln1_g : w.ln2_g, nullptr));
+      } else if (rest == "layer.1.DenseReluDense.wi.weight") {
+        if (!shape_is(shape, ndim, F, H)) return bad_shape(name_c);
+        OM_TRY(upload(data, kind, (size_t)F * H, nullptr, w.w1));
+      } else if (rest == "layer.1.DenseReluDense.wo.weight") {
+        if (!shape_is(shape, ndim, H, F)) return bad_shape(name_c);
+        OM_TRY(upload(data, kind, (size_t)H * F, nullptr, w.w2));
+      } else if (rest == "layer.1.DenseReluDense.wi_0.weight" || rest == "layer.1.DenseReluDense.wi_1.weight") {
+        return fail(OM_EINVAL, "gated-GELU T5 feed-forward (t5 v1.1) is not supported by this build");
+      } else {
+        return 1;
+      }
+    } else {
+      return 1;
+    }
+  }
+  return mark(e, name);
+}
+
+int om_encoder_finalize(om_encoder* e) {
+  if (!e) return fail(OM_EINVAL, "om_encoder_finalize: null encoder");
+  std::string miss;
+  int nmiss = 0;
+  for (auto& r : e->required)
+    if (!r.second) {
+      if (nmiss < 4) miss += (nmiss ? ", " : "") + r.first;
+      ++nmiss;
+    }
+  if (nmiss) return fail(OM_ESTATE, "om_encoder_finalize: %d parameter(s) missing: %s%s", nmiss, miss.c_str(), nmiss > 4 ? ", ..." : "");
+  if (e->d.arch == OM_ARCH_T5ENC) {
+    const int nh = e->d.heads, W = 2 * kMaxL - 1;
+    std::vector<float> table((size_t)nh * W);
+    for (int rel = -(kMaxL - 1); rel <= kMaxL - 1; ++rel) {
+      const int b = t5_bucket(rel, e->d.rel_buckets, e->d.rel_max_distance);
+      for (int h = 0; h < nh; ++h) table[(size_t)h * W + rel + kMaxL - 1] = e->rel_host[(size_t)b * nh + h] * kLog2e;
+    }
+    OM_CUDA(cudaMemcpy(e->relbias_log2, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+  }
+  static bool attr = false;
+  if (!attr) {
+    OM_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    attr = true;
+  }
+  e->finalized = true;
+  return 0;
+}
+
+int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_mask, const int64_t* token_type_ids,
+              int B, int L, void* out_reps, om_dtype out_dtype, int64_t out_row_stride, float* out_hidden, void* stream) {
+  if (!e || !input_ids || !attention_mask || !out_reps) return fail(OM_EINVAL, "om_encode: null argument");
+  if (!e->finalized) return fail(OM_ESTATE, "om_encode: call om_encoder_finalize first");
+  if (B <= 0 || L <= 0) return fail(OM_EINVAL, "om_encode: B and L must be positive");
+  if (L > kMaxL) return fail(OM_EINVAL, "om_encode: L=%d exceeds the supported maximum of %d tokens", L, kMaxL);
+  const om_encoder_desc& d = e->d;
+  if (d.arch == OM_ARCH_BERT && L > d.max_pos) return fail(OM_EINVAL, "om_encode: L=%d exceeds max_position_embeddings", L);
+  const int64_t T64 = static_cast<int64_t>(B) * L;
+  if (T64 > e->Tmax) return fail(OM_EINVAL, "om_encode: B*L=%lld exceeds max_batch_tokens=%d", (long long)T64, e->Tmax);
+  if (out_dtype != OM_F32 && out_dtype != OM_BF16) return fail(OM_EINVAL, "om_encode: out dtype must be f32 or bf16");
+  const int rep_dim = om_encoder_rep_dim(e);
+  if (out_row_stride < rep_dim) return fail(OM_EINVAL, "om_encode: out_row_stride < rep_dim");
+  const int sms = device_sm_count();
+  if (sms < 0) return sms;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = static_cast<int>(T64), H = d.hidden, I = e->I, F = d.ffn;
+  const bool bert = d.arch == OM_ARCH_BERT;
+  const int rows4 = (T + 3) / 4;
+
+  keymask_kernel<<<(T + 255) / 256, 256, 0, st>>>(attention_mask, e->kmask, T);
+  if (bert)
+    bert_embed_kernel<<<rows4, 128, 0, st>>>(input_ids, token_type_ids, e->word, e->type, e->pos, e->emb_g, e->emb_b,
+                                             d.ln_eps, T, L, H, d.vocab, std::max(d.type_vocab, 1), e->h, e->xb);
+  else
+    t5_embed_kernel<<<rows4, 128, 0, st>>>(input_ids, e->word, T, H, d.vocab, e->h);
+  OM_CUDA(cudaGetLastError());
+
+  // attention geometry
+  const int spt = L > 64 ? 1 : kMaxL / L;
+  AttnParams ap;
+  ap.T = T;
+  ap.L = L;
+  ap.spt = spt;
+  ap.I = I;
+  ap.Tvalid_rows = spt * L;
+  ap.scale_log2 = (bert ? 0.125f : 1.0f) * kLog2e;
+  ap.kmask = e->kmask;
+  ap.relbias_log2 = bert ? nullptr : e->relbias_log2;
+  ap.ctx = e->ctx;
+  const int n_tiles = (B + spt - 1) / spt;
+  CUtensorMap tmQK, tmVt;
+  if (make_tmap_bf16_2d(&tmQK, e->qk, (uint64_t)2 * I, (uint64_t)T, (uint64_t)2 * I * 2, 64, 128) != 0 ||
+      make_tmap_bf16_2d(&tmVt, e->vt, (uint64_t)T, (uint64_t)I, (uint64_t)e->Tld * 2, 64, 64) != 0)
+    return fail(OM_ECUDA, "om_encode: tensor map creation failed");
+
+  for (int li = 0; li < d.layers; ++li) {
+    const LayerW& w = e->layers[li];
+    if (!bert) norm_kernel<true><<<rows4, 128, 0, st>>>(e->h, w.ln1_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
+    {
+      EpiQKV epi{e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I};
+      cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
+      if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
+    }
+    attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
+    OM_CUDA(cudaGetLastError());
+    {
+      EpiStoreF32 epi{e->h, H, bert ? w.bo : nullptr, e->h, H, T, H};
+      cudaError_t err = launch_gemm<256, 4, false, 8>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st);
+      if (err != cudaSuccess) return fail(OM_ECUDA, "O-proj GEMM launch failed: %s", cudaGetErrorString(err));
+    }
+    if (bert)
+      norm_kernel<false><<<rows4, 128, 0, st>>>(e->h, w.ln1_g, w.ln1_b, d.ln_eps, T, H, e->h, e->xb);
+    else
+      norm_kernel<true><<<rows4, 128, 0, st>>>(e->h, w.ln2_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
+    {
+      cudaError_t err;
+      if (bert) {
+        EpiBiasActBf16<ACT_GELU> epi{e->inter, F, w.b1, T, F};
+        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
+      } else {
+        EpiBiasActBf16<ACT_RELU> epi{e->inter, F, nullptr, T, F};
+        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
+      }
+      if (err != cudaSuccess) return fail(OM_ECUDA, "FFN1 GEMM launch failed: %s", cudaGetErrorString(err));
+    }
+    {
+      EpiStoreF32 epi{e->h, H, bert ? w.b2 : nullptr, e->h, H, T, H};
+      cudaError_t err = launch_gemm<256, 4, false, 8>(e->inter, F, w.w2, F, T, H, F, epi, sms, st);
+      if (err != cudaSuccess) return fail(OM_ECUDA, "FFN2 GEMM launch failed: %s", cudaGetErrorString(err));
+    }
+    if (bert) norm_kernel<false><<<rows4, 128, 0, st>>>(e->h, w.ln2_g, w.ln2_b, d.ln_eps, T, H, e->h, e->xb);
+    OM_CUDA(cudaGetLastError());
+  }
+  if (!bert) norm_kernel<true><<<rows4, 128, 0, st>>>(e->h, e->final_g, nullptr, d.ln_eps, T, H, e->h, nullptr);
+  if (out_hidden)
+    OM_CUDA(cudaMemcpyAsync(out_hidden, e->h, static_cast<size_t>(T) * H * 4, cudaMemcpyDeviceToDevice, st));
+
+  pool_kernel<<<B, 256, 0, st>>>(e->h, attention_mask, L, H, d.pooling == OM_POOL_MEAN ? 1 : 0, e->pooled);
+  const float* reps = e->pooled;
+  if (d.has_head) {
+    const int warps = d.head_out * ((B + 7) / 8);
+    head_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(e->pooled, e->head_w, B, H, d.head_out, e->headed);
+    reps = e->headed;
+  }
+  if (out_dtype == OM_F32)
+    finish_reps_kernel<float><<<(B + 3) / 4, 128, 0, st>>>(reps, B, rep_dim, d.normalize, static_cast<float*>(out_reps),
+                                                          out_row_stride);
+  else
+    finish_reps_kernel<__nv_bfloat16><<<(B + 3) / 4, 128, 0, st>>>(reps, B, rep_dim, d.normalize,
+                                                                  static_cast<__nv_bfloat16*>(out_reps), out_row_stride);
+  OM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -7,7 +7,10 @@
 //   warp 1 (one elected lane)  MMA issuer   : tcgen05.mma 128 x BN x 16, accumulators in TMEM,
 //                                             double-buffered (2 x BN columns)
 //   warp 2                     TMEM allocator
-//   warps 4..7                 epilogue     : tcgen05.ld -> registers -> Epi functor (fused op)
+//   warps 4..4+EPI_WARPS       epilogue     : tcgen05.ld -> registers -> Epi functor (fused op).
+//                                             EPI_WARPS = 4: one thread per accumulator row; 8: two threads
+//                                             per row, each owning half of the tile's columns (for
+//                                             math-heavy epilogues such as bias + erf-GELU)
 //
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue); static persistent
 // tile schedule (tile = blockIdx.x + i * gridDim.x).
@@ -20,7 +23,7 @@ namespace om {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmProducerThreads = 128;  // warps 0..3: TMA, MMA, TMEM alloc, idle
 
 template <int BN, int STAGES>
 struct GemmCfg {
@@ -33,15 +36,18 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
 };
 
-// Epilogue functor contract (all methods __device__, called by the 128 epilogue threads; thread <-> row):
+// Epilogue functor contract (all methods __device__, called by the epilogue threads; thread <-> row (half)):
 //   struct State;                                             per-thread, per-tile scratch
 //   void begin(State&, int row, int m_blk, int n_blk) const;  once per tile
 //   void chunk(State&, int row, int col0, const float (&v)[32]) const;   v = C[row, col0 .. col0+31]
 //   void end(State&, int row) const;                           once per tile
+//   static constexpr int kPasses = 1;                          2: the accumulator tile is read twice,
+//        chunk(..., int pass) is called for pass 0 then pass 1 with between(State&, int row) in between
+//        (TMEM re-reads are cheap; used by the search filter to count survivors before appending them)
 // Rows >= M and columns >= N contain zeros (TMA out-of-bounds fill) and must be masked by the functor.
 
-template <int BN, int STAGES, bool M_FASTEST, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
+__global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, Epi epi) {
   using Cfg = GemmCfg<BN, STAGES>;
@@ -67,7 +73,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -138,7 +144,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS must be 4 or 8");
+    const int ew = (warp - 4) & 3;      // == warp % 4: the TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;   // column half owned by this warp when EPI_WARPS == 8
+    constexpr int kChunks = BN / 32 / (EPI_WARPS / 4);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
@@ -151,14 +160,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
+      for (int pass = 0; pass < Epi::kPasses; ++pass) {
+        if constexpr (Epi::kPasses > 1) {
+          if (pass > 0) epi.between(st, row);
+        }
+#pragma unroll 1
+        for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epi.chunk(st, row, n_blk * BN + c * 32, v);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if constexpr (Epi::kPasses > 1)
+            epi.chunk(st, row, n_blk * BN + c * 32, v, pass);
+          else
+            epi.chunk(st, row, n_blk * BN + c * 32, v);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -177,7 +195,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // Host launcher.  A: [M, K] bf16 row pitch lda elements; B: [N, K] bf16 row pitch ldb elements.
 // Returns cudaSuccess / a CUDA error; tensor-map failures map to cudaErrorInvalidValue.
-template <int BN, int STAGES, bool M_FASTEST, class Epi>
+template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
 static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                                       const Epi& epi, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, STAGES>;
@@ -187,7 +205,7 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
     return cudaErrorInvalidValue;
   if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, BN) != 0)
     return cudaErrorInvalidValue;
-  auto kern = gemm_bf16_tn_kernel<BN, STAGES, M_FASTEST, Epi>;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, M_FASTEST, EPI_WARPS, Epi>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -196,7 +214,7 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
   }
   const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, epi);
+  kern<<<grid, kGemmProducerThreads + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, epi);
   return cudaGetLastError();
 }
 
@@ -210,6 +228,7 @@ struct EpiStoreF32 {  // C fp32 = acc (+ bias[n]) (+ resid[m, n])
   const float* resid;  // nullable, [M, ldr]; may alias C
   int64_t ldr;
   int M, N;
+  static constexpr int kPasses = 1;
   struct State {};
   __device__ __forceinline__ void begin(State&, int, int, int) const {}
   __device__ __forceinline__ void end(State&, int) const {}

@@ -70,7 +70,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t site) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t site) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*reinterpret_cast<volatile unsigned int*>(&om_dev_fault) != 0u) return;

@@ -1,0 +1,634 @@
+// Exact inner-product top-k over an HBM-resident flat index — the B200 replacement of
+// faiss.IndexFlatIP.{add,search,reset} as the reference uses it
+// (src/openmatch/retriever/dense_retriever.py:38-41,105,133-137,180) and of the IndexShards merge behind
+// index_cpu_to_gpu_multiple(shard=True) (:43-58).
+//
+// Storage per index shard: fp32 master rows [n, d] (what index.add received; used for exact re-scoring)
+// plus a bf16 scan copy [n, dpad] (tensor-core operand).
+//
+// search(q, k):
+//   1. SCAN   bf16 Q * X^T on tcgen05 (gemm.cuh mainloop) with the top-k filter fused into the epilogue:
+//             scores never leave TMEM/registers; a thread owns one query row, compares its 32-column chunk
+//             against that query's running threshold and appends the rare survivors
+//             (key = orderable(score) << 32 | ~row) to the query's candidate list in HBM.
+//             The corpus is swept in rounds of doubling size; after each round
+//   2. SELECT a per-query bitonic sort in shared memory keeps the best kp = k + slack candidates and
+//             publishes the kp-th score as the next round's (strict) threshold.  Expected survivors per
+//             round ~ kp, so the list capacity C >= 2.5 kp + 512 is ample for exchangeable data; an overflow (e.g.
+//             adversarially sorted corpus) is detected and the query chunk is redone with an overflow-proof
+//             fixed-size round schedule, so the result is always exact w.r.t. the bf16 stage.
+//   3. FINAL  the kp candidates are re-scored against the fp32 master rows (fp32 FMA), sorted by
+//             (score desc, row asc) and the top k emitted as (D fp32, I int64) — faiss's output contract.
+#include <float.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.h"
+#include "gemm.cuh"
+
+namespace om {
+
+// ---------------------------------------------------------------------------------------------------
+// candidate keys: descending unsigned order == (score descending, row ascending)
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t f32_orderable(float s) {
+  s = s + 0.0f;  // -0 -> +0
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(s);
+#else
+  uint32_t u;
+  memcpy(&u, &s, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float f32_from_orderable(uint32_t u) {
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float s;
+  memcpy(&s, &u, 4);
+  return s;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned long long make_key(float s, uint32_t row) {
+  return (static_cast<unsigned long long>(f32_orderable(s)) << 32) | static_cast<unsigned long long>(0xffffffffu - row);
+}
+__host__ __device__ __forceinline__ uint32_t key_row(unsigned long long k) {
+  return 0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull);
+}
+__host__ __device__ __forceinline__ float key_score(unsigned long long k) {
+  return f32_from_orderable(static_cast<uint32_t>(k >> 32));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused scan epilogue
+// ---------------------------------------------------------------------------------------------------
+struct EpiScan {
+  const float* thr;          // [nq] strict lower bound per query
+  unsigned long long* cand;  // [nq, C]
+  int* count;                // [nq]
+  int* overflow;             // single flag
+  int nq, n_cols, C;
+  uint32_t row_base;  // corpus row of column 0 of this round
+  int dense;          // 1: first round, every score is stored at position = column
+  // Two passes over the accumulator tile: pass 0 counts this thread's survivors, between() reserves their
+  // slots with ONE atomicAdd per (thread, tile) — an append per survivor would stall the warp for a full
+  // L2 round trip each time — and pass 1 re-reads TMEM and stores the keys (fire-and-forget stores).
+  static constexpr int kPasses = 2;
+  struct State {
+    float t;
+    int n, pos;
+  };
+  __device__ __forceinline__ void begin(State& s, int row, int, int) const {
+    s.t = (row < nq && !dense) ? thr[row] : __int_as_float(0x7f800000);
+    s.n = 0;
+    s.pos = 0;
+  }
+  __device__ __forceinline__ void end(State&, int) const {}
+  __device__ __forceinline__ void between(State& s, int row) const {
+    if (s.n > 0) {
+      s.pos = atomicAdd(count + row, s.n);
+      if (s.pos + s.n > C) *overflow = 1;
+    }
+  }
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int pass) const {
+    if (row >= nq || col0 >= n_cols) return;
+    unsigned long long* mine = cand + static_cast<size_t>(row) * C;
+    if (dense) {
+      if (pass != 0) return;
+      if (col0 + 32 <= n_cols) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          ulonglong2 kk;
+          kk.x = make_key(v[i], row_base + col0 + i);
+          kk.y = make_key(v[i + 1], row_base + col0 + i + 1);
+          *reinterpret_cast<ulonglong2*>(mine + col0 + i) = kk;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < n_cols) mine[col0 + i] = make_key(v[i], row_base + col0 + i);
+      }
+      return;
+    }
+    const float t = s.t;
+    const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
+    if (pass == 0) {
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) n += (v[i] > t && i < lim) ? 1 : 0;
+      s.n += n;
+    } else {
+      if (s.n == 0) return;
+      int pos = s.pos;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (v[i] > t && i < lim) {
+          if (pos < C) mine[pos] = make_key(v[i], row_base + col0 + i);
+          ++pos;
+        }
+      }
+      s.pos = pos;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory bitonic sort (descending) of P = 2^m keys by nthreads threads
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* s, int P, int tid, int nthreads) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += nthreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // insert a 0 bit at position log2(j)
+        const int p = i | j;
+        const unsigned long long a = s[i], b = s[p];
+        const bool desc = (i & k) == 0;
+        if ((a < b) == desc) {
+          s[i] = b;
+          s[p] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// SELECT: one CTA per query.  Keeps the best min(cnt, kp) candidates (sorted) at the head of the list and
+// publishes the kp-th score as the new strict threshold.
+__global__ void __launch_bounds__(512) select_kernel(unsigned long long* cand, int* count, float* thr, int C, int kp,
+                                                     int cnt_override) {
+  extern __shared__ unsigned long long skeys[];
+  const int q = blockIdx.x;
+  unsigned long long* mine = cand + static_cast<size_t>(q) * C;
+  int cnt = cnt_override >= 0 ? cnt_override : count[q];
+  cnt = cnt < C ? cnt : C;
+  int P = 1;
+  while (P < cnt) P <<= 1;
+  if (P < 2) P = 2;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < cnt ? mine[i] : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(skeys, P, threadIdx.x, blockDim.x);
+  const int keep = cnt < kp ? cnt : kp;
+  for (int i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = skeys[i];
+  if (threadIdx.x == 0) {
+    count[q] = keep;
+    thr[q] = cnt >= kp ? key_score(skeys[kp - 1]) : __int_as_float(0xff800000);
+  }
+}
+
+// FINAL: one CTA per query: exact fp32 re-score of the surviving candidates against the master rows,
+// sort by (score desc, row asc), emit top-k.
+__global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long* cand, const int* count, int C,
+                                                       const float* __restrict__ qf, const float* __restrict__ xf,
+                                                       int d, int k, float* D, int64_t* I, int64_t id_offset) {
+  extern __shared__ unsigned long long fsm[];
+  const int q = blockIdx.x;
+  int cnt = count[q];
+  int P = 2;
+  while (P < cnt) P <<= 1;
+  unsigned long long* skeys = fsm;
+  float* sq = reinterpret_cast<float*>(fsm + P);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) sq[i] = qf[static_cast<size_t>(q) * d + i];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = 0ull;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const unsigned long long* mine = cand + static_cast<size_t>(q) * C;
+  for (int j = warp; j < cnt; j += nw) {
+    const uint32_t row = key_row(mine[j]);
+    const float* x = xf + static_cast<size_t>(row) * d;
+    float acc = 0.f;
+    if ((d & 3) == 0) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      const float4* q4 = reinterpret_cast<const float4*>(sq);
+      for (int i = lane; i < (d >> 2); i += 32) {
+        const float4 a = __ldg(x4 + i), b = q4[i];
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) acc = fmaf(__ldg(x + i), sq[i], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) skeys[j] = make_key(acc, row);
+  }
+  __syncthreads();
+  bitonic_sort_desc(skeys, P, threadIdx.x, blockDim.x);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    float s = -FLT_MAX;
+    int64_t id = -1;
+    if (r < cnt) {
+      s = key_score(skeys[r]);
+      id = id_offset + static_cast<int64_t>(key_row(skeys[r]));
+    }
+    D[static_cast<size_t>(q) * k + r] = s;
+    I[static_cast<size_t>(q) * k + r] = id;
+  }
+}
+
+// fp32 [n, d] -> bf16 [n, dpad] (pad columns zeroed)
+__global__ void f32_to_bf16_rows(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n, int d,
+                                 int dpad) {
+  const int64_t total = n * static_cast<int64_t>(dpad);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dpad;
+    const int c = static_cast<int>(i - r * dpad);
+    dst[i] = __float2bfloat16(c < d ? src[r * d + c] : 0.f);
+  }
+}
+template <typename T>
+__global__ void to_f32(const T* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<float>(src[i]);
+}
+__global__ void fill_i32(int* p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// MERGE (sharded search exchange step): one CTA per query over nparts * k candidates.
+__global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64_t* Ip, int nparts, int nq, int k,
+                                                    float* D, int64_t* I) {
+  // keys: orderable(score) << 32 | ~slot, with ties broken by id through a second pass on equal scores
+  extern __shared__ unsigned long long msm[];
+  const int q = blockIdx.x;
+  const int total = nparts * k;
+  int P = 2;
+  while (P < total) P <<= 1;
+  unsigned long long* skeys = msm;           // [P] (score, slot)
+  int64_t* sid = reinterpret_cast<int64_t*>(msm + P);  // [total]
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < total) {
+      const int part = i / k, r = i - part * k;
+      const size_t off = (static_cast<size_t>(part) * nq + q) * k + r;
+      const int64_t id = Ip[off];
+      sid[i] = id;
+      if (id >= 0) key = (static_cast<unsigned long long>(f32_orderable(Dp[off])) << 32) | (0xffffffffu - i);
+    }
+    skeys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_desc(skeys, P, threadIdx.x, blockDim.x);
+  // Shards hold disjoint, increasing id ranges and each shard list is already (score desc, id asc), so slot
+  // order == id order among equal scores: the (score, slot) sort is the (score, id) sort.
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    const unsigned long long key = r < P ? skeys[r] : 0ull;
+    float s = -FLT_MAX;
+    int64_t id = -1;
+    if (key != 0ull) {
+      s = f32_from_orderable(static_cast<uint32_t>(key >> 32));
+      id = sid[0xffffffffu - static_cast<uint32_t>(key & 0xffffffffull)];
+    }
+    D[static_cast<size_t>(q) * k + r] = s;
+    I[static_cast<size_t>(q) * k + r] = id;
+  }
+}
+
+}  // namespace om
+
+using namespace om;
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct om_index {
+  int d = 0, dpad = 0;
+  int64_t n = 0, cap = 0;
+  float* xf = nullptr;
+  __nv_bfloat16* xb = nullptr;
+  int64_t rescore_slack = -1;
+  int force_safe = 0;
+  int64_t st_rounds = 0, st_retries = 0, st_capacity = 0;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+static int index_grow(om_index* ix, int64_t need) {
+  if (need <= ix->cap) return 0;
+  int64_t ncap = std::max<int64_t>(need, ix->cap + ix->cap / 2);
+  ncap = round_up(std::max<int64_t>(ncap, 1024), 256);
+  float* nxf = nullptr;
+  __nv_bfloat16* nxb = nullptr;
+  OM_CUDA(cudaMalloc(&nxf, static_cast<size_t>(ncap) * ix->d * sizeof(float)));
+  cudaError_t e = cudaMalloc(&nxb, static_cast<size_t>(ncap) * ix->dpad * sizeof(__nv_bfloat16));
+  if (e != cudaSuccess) {
+    cudaFree(nxf);
+    cudaGetLastError();
+    return fail(OM_ENOMEM, "index: cannot allocate bf16 scan copy for %lld rows", (long long)ncap);
+  }
+  if (ix->n > 0) {
+    OM_CUDA(cudaMemcpy(nxf, ix->xf, static_cast<size_t>(ix->n) * ix->d * sizeof(float), cudaMemcpyDeviceToDevice));
+    OM_CUDA(cudaMemcpy(nxb, ix->xb, static_cast<size_t>(ix->n) * ix->dpad * sizeof(__nv_bfloat16),
+                       cudaMemcpyDeviceToDevice));
+  }
+  cudaFree(ix->xf);
+  cudaFree(ix->xb);
+  ix->xf = nxf;
+  ix->xb = nxb;
+  ix->cap = ncap;
+  return 0;
+}
+
+static int ws_reserve(om_index* ix, size_t bytes) {
+  if (bytes <= ix->ws_bytes) return 0;
+  if (ix->ws) cudaFree(ix->ws);
+  ix->ws = nullptr;
+  ix->ws_bytes = 0;
+  OM_CUDA(cudaMalloc(&ix->ws, bytes));
+  ix->ws_bytes = bytes;
+  return 0;
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  return static_cast<int>(std::min<int64_t>(std::max<int64_t>(g, 1), 148 * 16));
+}
+
+extern "C" {
+
+int om_index_create(int d, om_index** out) {
+  if (!out || d <= 0) return fail(OM_EINVAL, "om_index_create: d must be positive");
+  OM_TRY(device_sm_count());
+  om_index* ix = new (std::nothrow) om_index();
+  if (!ix) return fail(OM_ENOMEM, "om_index_create: out of host memory");
+  ix->d = d;
+  ix->dpad = static_cast<int>(round_up(d, 8));  // 16-byte row pitch for TMA
+  *out = ix;
+  return 0;
+}
+
+void om_index_destroy(om_index* ix) {
+  if (!ix) return;
+  cudaFree(ix->xf);
+  cudaFree(ix->xb);
+  cudaFree(ix->ws);
+  delete ix;
+}
+
+int64_t om_index_ntotal(const om_index* ix) { return ix ? ix->n : 0; }
+int om_index_dim(const om_index* ix) { return ix ? ix->d : 0; }
+
+int om_index_reset(om_index* ix) {
+  if (!ix) return fail(OM_EINVAL, "om_index_reset: null index");
+  ix->n = 0;
+  return 0;
+}
+
+int om_index_reserve(om_index* ix, int64_t n, float** dev_rows) {
+  if (!ix || n < 0 || !dev_rows) return fail(OM_EINVAL, "om_index_reserve: bad arguments");
+  if (ix->n + n > 0xfffffff0ll) return fail(OM_EINVAL, "index shard limited to 2^32-16 rows; shard the corpus");
+  OM_TRY(index_grow(ix, ix->n + n));
+  *dev_rows = ix->xf + static_cast<size_t>(ix->n) * ix->d;
+  return 0;
+}
+
+int om_index_commit(om_index* ix, int64_t n, void* stream) {
+  if (!ix || n < 0 || ix->n + n > ix->cap) return fail(OM_EINVAL, "om_index_commit: more rows than reserved");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  f32_to_bf16_rows<<<grid_for(n * ix->dpad, 256), 256, 0, st>>>(ix->xf + static_cast<size_t>(ix->n) * ix->d,
+                                                               ix->xb + static_cast<size_t>(ix->n) * ix->dpad, n,
+                                                               ix->d, ix->dpad);
+  OM_CUDA(cudaGetLastError());
+  ix->n += n;
+  return 0;
+}
+
+int om_index_add(om_index* ix, const void* x, om_memkind kind, om_dtype dtype, int64_t n, void* stream) {
+  if (!ix || (!x && n > 0) || n < 0) return fail(OM_EINVAL, "om_index_add: bad arguments");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dst = nullptr;
+  OM_TRY(om_index_reserve(ix, n, &dst));
+  const size_t elems = static_cast<size_t>(n) * ix->d;
+  if (dtype == OM_F32) {
+    OM_CUDA(cudaMemcpyAsync(dst, x, elems * 4, kind == OM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                            st));
+  } else if (dtype == OM_BF16 || dtype == OM_F16) {
+    const void* src = x;
+    void* tmp = nullptr;
+    if (kind == OM_HOST) {
+      OM_CUDA(cudaMalloc(&tmp, elems * 2));
+      OM_CUDA(cudaMemcpyAsync(tmp, x, elems * 2, cudaMemcpyHostToDevice, st));
+      src = tmp;
+    }
+    if (dtype == OM_BF16)
+      to_f32<<<grid_for(elems, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst, (int64_t)elems);
+    else
+      to_f32<<<grid_for(elems, 256), 256, 0, st>>>(static_cast<const __half*>(src), dst, (int64_t)elems);
+    OM_CUDA(cudaGetLastError());
+    if (tmp) {
+      OM_CUDA(cudaStreamSynchronize(st));
+      cudaFree(tmp);
+    }
+  } else {
+    return fail(OM_EINVAL, "om_index_add: unsupported dtype %d", (int)dtype);
+  }
+  OM_TRY(om_index_commit(ix, n, stream));
+  if (kind == OM_HOST) OM_CUDA(cudaStreamSynchronize(st));  // caller may free / reuse its host buffer
+  return 0;
+}
+
+int om_index_set_param(om_index* ix, const char* name, int64_t value) {
+  if (!ix || !name) return fail(OM_EINVAL, "om_index_set_param: bad arguments");
+  if (!strcmp(name, "rescore_slack")) {
+    ix->rescore_slack = value;
+  } else if (!strcmp(name, "force_safe_rounds")) {
+    ix->force_safe = value != 0;
+  } else {
+    return fail(OM_EINVAL, "om_index_set_param: unknown parameter '%s'", name);
+  }
+  return 0;
+}
+
+int64_t om_index_get_stat(const om_index* ix, const char* name) {
+  if (!ix || !name) return -1;
+  if (!strcmp(name, "rounds")) return ix->st_rounds;
+  if (!strcmp(name, "overflow_retries")) return ix->st_retries;
+  if (!strcmp(name, "candidates")) return ix->st_capacity;
+  return -1;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct ChunkWs {
+  unsigned long long* cand;
+  int* count;
+  float* thr;
+  int* overflow;
+};
+
+// One sweep of the corpus for a chunk of queries.  safe=false: doubling rounds; safe=true: fixed rounds of
+// C - kp rows, which cannot overflow.
+int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, const ChunkWs& w, bool safe, int sms,
+          cudaStream_t st) {
+  const int64_t N = ix->n;
+  OM_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
+  int64_t pos = 0;
+  const size_t sel_smem = static_cast<size_t>(C) * 8;
+  static bool sel_attr = false;
+  if (!sel_attr) {
+    OM_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    sel_attr = true;
+  }
+  bool first = true;
+  while (pos < N) {
+    int64_t step;
+    if (first)
+      step = std::min<int64_t>(N, C);
+    else if (safe)
+      step = std::min<int64_t>(N - pos, std::max<int64_t>(256, ((C - kp) / 256) * 256));
+    else
+      step = std::min<int64_t>(N - pos, pos);
+    EpiScan epi;
+    epi.thr = w.thr;
+    epi.cand = w.cand;
+    epi.count = w.count;
+    epi.overflow = w.overflow;
+    epi.nq = nq;
+    epi.n_cols = static_cast<int>(step);
+    epi.C = C;
+    epi.row_base = static_cast<uint32_t>(pos);
+    epi.dense = first ? 1 : 0;
+    cudaError_t e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, ix->xb + static_cast<size_t>(pos) * ix->dpad, ix->dpad,
+                                              nq, static_cast<int>(step), ix->d, epi, sms, st);
+    if (e != cudaSuccess) return fail(OM_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
+    select_kernel<<<nq, 512, sel_smem, st>>>(w.cand, w.count, w.thr, C, kp, first ? static_cast<int>(step) : -1);
+    OM_CUDA(cudaGetLastError());
+    pos += step;
+    first = false;
+    ix->st_rounds++;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
+                               om_memkind out_kind, int64_t id_offset, void* stream) {
+  if (!ix || (nq > 0 && (!q || !D || !I)) || nq < 0 || k <= 0)
+    return fail(OM_EINVAL, "om_index_search: bad arguments (nq=%d k=%d)", nq, k);
+  if (nq == 0) return 0;
+  const int sms = device_sm_count();
+  if (sms < 0) return sms;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = ix->d, dpad = ix->dpad;
+  int64_t slack = ix->rescore_slack >= 0 ? ix->rescore_slack : std::max<int64_t>(64, k / 8);
+  const int64_t kp64 = std::min<int64_t>(static_cast<int64_t>(k) + slack, std::max<int64_t>(ix->n, 1));
+  if (kp64 > 4096) return fail(OM_EINVAL, "om_index_search: k + slack = %lld exceeds 4096", (long long)kp64);
+  const int kp = static_cast<int>(kp64);
+  // Expected list length after a doubling round is ~2 kp (kp kept + ~kp new survivors, sd ~ sqrt(2 kp)).
+  int C = 1024;
+  while (C < (5 * kp) / 2 + 512) C <<= 1;
+  ix->st_capacity = C;
+  ix->st_rounds = 0;
+  ix->st_retries = 0;
+
+  const int QCHUNK = 16384;
+  const int nqc_max = std::min(nq, QCHUNK);
+  // workspace layout
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off += round_up(bytes, 256);
+    return o;
+  };
+  const size_t o_qf = carve(static_cast<size_t>(nq) * d * 4);
+  const size_t o_qb = carve(static_cast<size_t>(nq) * dpad * 2);
+  const size_t o_cand = carve(static_cast<size_t>(nqc_max) * C * 8);
+  const size_t o_count = carve(static_cast<size_t>(nqc_max) * 4);
+  const size_t o_thr = carve(static_cast<size_t>(nqc_max) * 4);
+  const size_t o_ovf = carve(256);
+  const size_t o_D = carve(out_kind == OM_HOST ? static_cast<size_t>(nq) * k * 4 : 0);
+  const size_t o_I = carve(out_kind == OM_HOST ? static_cast<size_t>(nq) * k * 8 : 0);
+  OM_TRY(ws_reserve(ix, off));
+  uint8_t* base = static_cast<uint8_t*>(ix->ws);
+  float* qf = reinterpret_cast<float*>(base + o_qf);
+  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(base + o_qb);
+  ChunkWs w{reinterpret_cast<unsigned long long*>(base + o_cand), reinterpret_cast<int*>(base + o_count),
+            reinterpret_cast<float*>(base + o_thr), reinterpret_cast<int*>(base + o_ovf)};
+  float* dD = out_kind == OM_HOST ? reinterpret_cast<float*>(base + o_D) : D;
+  int64_t* dI = out_kind == OM_HOST ? reinterpret_cast<int64_t*>(base + o_I) : I;
+
+  OM_CUDA(cudaMemcpyAsync(qf, q, static_cast<size_t>(nq) * d * 4,
+                          q_kind == OM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  f32_to_bf16_rows<<<grid_for(static_cast<int64_t>(nq) * dpad, 256), 256, 0, st>>>(qf, qb, nq, d, dpad);
+  OM_CUDA(cudaGetLastError());
+
+  static bool fin_attr = false;
+  if (!fin_attr) {
+    OM_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 8 + 65536));
+    fin_attr = true;
+  }
+  int P2 = 2;
+  while (P2 < kp) P2 <<= 1;
+  const size_t fin_smem = static_cast<size_t>(P2) * 8 + static_cast<size_t>(d) * 4;
+  if (d > 16384) return fail(OM_EINVAL, "om_index_search: d > 16384 unsupported");
+
+  for (int q0 = 0; q0 < nq; q0 += QCHUNK) {
+    const int nqc = std::min(QCHUNK, nq - q0);
+    bool safe = ix->force_safe != 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (ix->n == 0) {
+        fill_i32<<<(nqc + 255) / 256, 256, 0, st>>>(w.count, 0, nqc);
+        OM_CUDA(cudaGetLastError());
+      } else {
+        OM_TRY(sweep(ix, qb + static_cast<size_t>(q0) * dpad, nqc, kp, C, w, safe, sms, st));
+      }
+      finalize_kernel<<<nqc, 256, fin_smem, st>>>(w.cand, w.count, C, qf + static_cast<size_t>(q0) * d, ix->xf, d, k,
+                                                  dD + static_cast<size_t>(q0) * k, dI + static_cast<size_t>(q0) * k,
+                                                  id_offset);
+      OM_CUDA(cudaGetLastError());
+      int ovf = 0;
+      if (ix->n > 0) {
+        OM_CUDA(cudaMemcpyAsync(&ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OM_CUDA(cudaStreamSynchronize(st));
+        const unsigned int fault = read_clear_dev_fault();
+        if (fault) return fail(OM_EFAULT, "scan kernel pipeline fault 0x%08x", fault);
+      }
+      if (!ovf) break;
+      if (safe) return fail(OM_EFAULT, "candidate list overflow in the overflow-proof schedule (bug)");
+      safe = true;
+      ix->st_retries++;
+    }
+  }
+  if (out_kind == OM_HOST) {
+    OM_CUDA(cudaMemcpyAsync(D, dD, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+    OM_CUDA(cudaMemcpyAsync(I, dI, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+  }
+  OM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int om_topk_merge(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k, float* D,
+                             int64_t* I, void* stream) {
+  if (nparts <= 0 || nq < 0 || k <= 0 || !D_parts || !I_parts || !D || !I)
+    return fail(OM_EINVAL, "om_topk_merge: bad arguments");
+  if (nq == 0) return 0;
+  OM_TRY(device_sm_count());
+  const int64_t total = static_cast<int64_t>(nparts) * k;
+  if (total > 8192) return fail(OM_EINVAL, "om_topk_merge: nparts * k = %lld exceeds 8192", (long long)total);
+  int P = 2;
+  while (P < total) P <<= 1;
+  const size_t smem = static_cast<size_t>(P) * 8 + static_cast<size_t>(total) * 8;
+  static bool attr = false;
+  if (!attr) {
+    OM_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+    attr = true;
+  }
+  merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(D_parts, I_parts, nparts, nq, k, D, I);
+  OM_CUDA(cudaGetLastError());
+  return 0;
+}

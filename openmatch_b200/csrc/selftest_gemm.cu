@@ -32,6 +32,7 @@ struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics 
   unsigned long long* counter;
   float thr;
   int M, N;
+  static constexpr int kPasses = 1;
   struct State {
     int cnt;
   };
@@ -45,9 +46,9 @@ struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics 
   }
 };
 
-template <int BN, int STAGES, bool MF>
+template <int BN, int STAGES, bool MF, int EW = 4>
 static int check_case(int M, int N, int K, int num_sms, const char* dump_dir) {
-  printf("[case] BN=%d STAGES=%d M_FASTEST=%d  M=%d N=%d K=%d ... ", BN, STAGES, (int)MF, M, N, K);
+  printf("[case] BN=%d STAGES=%d M_FASTEST=%d EW=%d  M=%d N=%d K=%d ... ", BN, STAGES, (int)MF, EW, M, N, K);
   fflush(stdout);
   std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
   std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
@@ -68,7 +69,7 @@ static int check_case(int M, int N, int K, int num_sms, const char* dump_dir) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
-  cudaError_t e = launch_gemm<BN, STAGES, MF>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  cudaError_t e = launch_gemm<BN, STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
   if (e != cudaSuccess) {
     printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
     return 1;
@@ -119,7 +120,7 @@ static int check_case(int M, int N, int K, int num_sms, const char* dump_dir) {
   return bad ? 1 : 0;
 }
 
-template <int BN, int STAGES, bool MF>
+template <int BN, int STAGES, bool MF, int EW = 4>
 static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters) {
   __nv_bfloat16 *dA, *dB;
   unsigned long long* dcnt;
@@ -140,10 +141,10 @@ static void perf_case(const char* name, int M, int N, int K, int num_sms, int it
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 2; ++i) CK((launch_gemm<BN, STAGES, MF>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm<BN, STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm<BN, STAGES, MF>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm<BN, STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -171,6 +172,8 @@ int main(int argc, char** argv) {
   fails += check_case<64, 4, false>(200, 200, 128, sms, dump_dir);
   fails += check_case<256, 4, true>(1000, 3000, 768, sms, dump_dir);   // > 1 tile per CTA, both acc buffers
   fails += check_case<256, 4, false>(2048, 2304, 768, sms, dump_dir);  // many tiles per CTA
+  fails += check_case<256, 4, false, 8>(2048, 2304, 768, sms, dump_dir);  // 8 epilogue warps
+  fails += check_case<64, 4, false, 8>(300, 200, 128, sms, dump_dir);
   if (fails) {
     printf("SELFTEST FAILED (%d cases)\n", fails);
     return 1;

@@ -1,0 +1,192 @@
+"""HBM-resident exact inner-product index: the drop-in for ``faiss.IndexFlatIP`` as the reference uses it
+(``src/openmatch/retriever/dense_retriever.py:38-41`` construct, ``:105`` add, ``:133-137`` reset,
+``:180`` search) plus the row-sharded multi-GPU search that replaces
+``faiss.index_cpu_to_gpu_multiple(shard=True)`` (``:43-58``).
+
+All arithmetic runs in libopenmatch_b200.so (csrc/search.cu); this file only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class FlatIPIndex:
+    """``faiss.IndexFlatIP`` duck type (``d``, ``ntotal``, ``add``, ``search``, ``reset``) living on the
+    current CUDA device."""
+
+    def __init__(self, d: int):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.om_index_create(int(d), ctypes.byref(h)))
+        self._h = h
+        self.d = int(d)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.om_index_destroy(h)
+
+    # ---- faiss surface ----
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.om_index_ntotal(self._h))
+
+    def add(self, x) -> None:
+        """x: float32 [n, d]; numpy (host) or torch tensor (host or CUDA)."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            x = x.contiguous()
+            if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+                x = x.float()
+            dt = {torch.float32: _lib.OM_F32, torch.bfloat16: _lib.OM_BF16, torch.float16: _lib.OM_F16}[x.dtype]
+            self._check_shape(x.shape)
+            _lib.check(self._lib.om_index_add(self._h, x.data_ptr(), _lib.OM_DEVICE, dt, x.shape[0], _stream()))
+            torch.cuda.current_stream().synchronize()  # the caller's tensor may be freed right after
+            return
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self._check_shape(x.shape)
+        _lib.check(self._lib.om_index_add(self._h, x.ctypes.data, _lib.OM_HOST, _lib.OM_F32, x.shape[0], _stream()))
+
+    def reset(self) -> None:
+        _lib.check(self._lib.om_index_reset(self._h))
+
+    def search(self, q, k: int, id_offset: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """``D, I = index.search(q, k)`` with numpy outputs (float32 [nq, k], int64 [nq, k])."""
+        if isinstance(q, torch.Tensor) and q.is_cuda:
+            D, I = self.search_device(q, k, id_offset)
+            return D.cpu().numpy(), I.cpu().numpy()
+        if isinstance(q, torch.Tensor):
+            q = q.detach().cpu().numpy()
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        self._check_shape(q.shape)
+        nq = q.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        _lib.check(self._lib.om_index_search(self._h, q.ctypes.data, _lib.OM_HOST, nq, int(k), D.ctypes.data,
+                                             I.ctypes.data, _lib.OM_HOST, int(id_offset), _stream()))
+        return D, I
+
+    # ---- device-resident variants ----
+    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        q = q.contiguous().float()
+        self._check_shape(q.shape)
+        nq = q.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        _lib.check(self._lib.om_index_search(self._h, q.data_ptr(), _lib.OM_DEVICE, nq, int(k), D.data_ptr(),
+                                             I.data_ptr(), _lib.OM_DEVICE, int(id_offset), _stream()))
+        return D, I
+
+    def search_pinned(self, q_host: torch.Tensor, k: int, D_host: torch.Tensor, I_host: torch.Tensor,
+                      id_offset: int = 0) -> None:
+        """Host (pinned) in, host (pinned) out — the end-to-end call the benchmark times."""
+        nq = q_host.shape[0]
+        _lib.check(self._lib.om_index_search(self._h, q_host.data_ptr(), _lib.OM_HOST, nq, int(k), D_host.data_ptr(),
+                                             I_host.data_ptr(), _lib.OM_HOST, int(id_offset), _stream()))
+
+    def reserve_rows(self, n: int) -> torch.Tensor:
+        """Zero-copy ingest: a float32 CUDA tensor view [n, d] of the next n rows of the shard; fill it
+        (e.g. as the encoder's output buffer) and call ``commit_rows(n)``."""
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.om_index_reserve(self._h, int(n), ctypes.byref(p)))
+        return _wrap_device_f32(p.value, (int(n), self.d))
+
+    def commit_rows(self, n: int) -> None:
+        _lib.check(self._lib.om_index_commit(self._h, int(n), _stream()))
+
+    def set_param(self, name: str, value: int) -> None:
+        _lib.check(self._lib.om_index_set_param(self._h, name.encode(), int(value)))
+
+    def stat(self, name: str) -> int:
+        return int(self._lib.om_index_get_stat(self._h, name.encode()))
+
+    def _check_shape(self, shape):
+        if len(shape) != 2 or shape[1] != self.d:
+            raise ValueError("expected a [n, %d] matrix, got %s" % (self.d, tuple(shape)))
+
+
+class _CudaArrayView:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _wrap_device_f32(ptr: int, shape) -> torch.Tensor:
+    return torch.as_tensor(_CudaArrayView(ptr, shape), device="cuda")
+
+
+def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[nparts, nq, k] per-shard results (shards in increasing id order) -> global (D, I) [nq, k]."""
+    lib = _lib.load()
+    nparts, nq, kk = D_parts.shape
+    assert kk == k and I_parts.shape == D_parts.shape
+    D_parts = D_parts.contiguous().float()
+    I_parts = I_parts.contiguous().long()
+    D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
+    _lib.check(lib.om_topk_merge(D_parts.data_ptr(), I_parts.data_ptr(), nparts, nq, k, D.data_ptr(), I.data_ptr(),
+                                 _stream()))
+    return D, I
+
+
+class ShardedFlatIPIndex:
+    """Row-sharded index: rank r of ``torch.distributed`` holds rows [offset_r, offset_r + n_r) in its own
+    HBM.  ``search`` = replicate queries -> local fused scan/top-k with global ids -> all-gather of the
+    per-shard [nq, k] (score, id) lists over NCCL/NVLink -> merge (score desc, id asc) on every rank."""
+
+    def __init__(self, d: int, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.local = FlatIPIndex(d)
+        self.d = d
+        self.offset = 0
+        self._ntotal = 0
+
+    def add_local(self, x) -> None:
+        self.local.add(x)
+
+    def finalize_offsets(self) -> None:
+        """Call once after all ranks added their rows: computes global id offsets (rank-major)."""
+        n_local = torch.tensor([self.local.ntotal], dtype=torch.int64, device="cuda")
+        if self.world > 1:
+            all_n = [torch.zeros_like(n_local) for _ in range(self.world)]
+            self.dist.all_gather(all_n, n_local, group=self.group)
+            counts = [int(t.item()) for t in all_n]
+        else:
+            counts = [int(n_local.item())]
+        self.offset = sum(counts[: self.rank])
+        self._ntotal = sum(counts)
+
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    def search_device(self, q: torch.Tensor, k: int):
+        Dl, Il = self.local.search_device(q, k, id_offset=self.offset)
+        if self.world == 1:
+            return Dl, Il
+        Dp = torch.empty((self.world,) + tuple(Dl.shape), dtype=Dl.dtype, device=Dl.device)
+        Ip = torch.empty((self.world,) + tuple(Il.shape), dtype=Il.dtype, device=Il.device)
+        self.dist.all_gather_into_tensor(Dp, Dl, group=self.group)
+        self.dist.all_gather_into_tensor(Ip, Il, group=self.group)
+        return merge_topk_device(Dp, Ip, k)
+
+    def search(self, q, k: int):
+        if not isinstance(q, torch.Tensor):
+            q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        D, I = self.search_device(q.cuda(), k)
+        return D.cpu().numpy(), I.cpu().numpy()

@@ -1,0 +1,168 @@
+"""GPU parity: libopenmatch_b200 index (through the C ABI) vs the CPU oracle (oracle/flat_index.py).
+
+Integer-valued data => every product/partial sum is exact in bf16 x bf16 -> fp32 and in fp32, so ids AND
+scores must match the oracle bit for bit, including the (score desc, row asc) tie order.  Gaussian data =>
+eps-tie-aware comparison against float64 scores (tolerance stated at each assert)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def om():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from openmatch_b200 import index as om_index
+    return om_index
+
+
+def _int_data(rng, n, d, lo=-8, hi=8):
+    return rng.integers(lo, hi + 1, size=(n, d)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 64, 37, 1), (20000, 64, 37, 10), (20000, 64, 37, 100),
+                                       (20000, 64, 37, 1000), (5000, 768, 130, 100), (3000, 100, 5, 7),
+                                       (257, 72, 3, 50)])
+def test_integer_data_exact(om, n, d, nq, k):
+    rng = np.random.default_rng(n + d + k)
+    x, q = _int_data(rng, n, d), _int_data(rng, nq, d)
+    idx = om.FlatIPIndex(d)
+    idx.add(x)
+    D, I = idx.search(q, k)
+    D0, I0 = oracle.flat_ip_search(q, x, k)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+
+
+def test_massive_ties(om):
+    # scores take only a handful of distinct values: tie order (row ascending) decides almost every rank
+    rng = np.random.default_rng(7)
+    x, q = _int_data(rng, 30000, 64, 0, 1), _int_data(rng, 9, 64, 0, 1)
+    idx = om.FlatIPIndex(64)
+    idx.add(x)
+    for k in (1, 64, 1000):
+        D, I = idx.search(q, k)
+        D0, I0 = oracle.flat_ip_search(q, x, k)
+        np.testing.assert_array_equal(I, I0)
+        np.testing.assert_array_equal(D, D0)
+
+
+def test_incremental_add_reset_and_padding(om):
+    rng = np.random.default_rng(3)
+    x, q = _int_data(rng, 700, 64), _int_data(rng, 4, 64)
+    idx = om.FlatIPIndex(64)
+    assert idx.ntotal == 0
+    D, I = idx.search(q, 5)  # empty index: all padding
+    assert (I == -1).all() and (D == oracle.flat_index.NEG_FILL).all()
+    idx.add(x[:100]); idx.add(x[100:101]); idx.add(torch.from_numpy(x[101:]).cuda())
+    assert idx.ntotal == 700
+    D, I = idx.search(q, 20)
+    D0, I0 = oracle.flat_ip_search(q, x, 20)
+    np.testing.assert_array_equal(I, I0)
+    idx.reset()
+    assert idx.ntotal == 0
+    idx.add(x[:6])
+    D, I = idx.search(q, 10)  # k > ntotal: tail padded with -1 / lowest(float) like faiss
+    D0, I0 = oracle.flat_ip_search(q, x[:6], 10)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+
+
+def test_sorted_corpus_forces_overflow_retry(om):
+    # adversarial order: every later row beats every earlier row for every query -> the doubling schedule
+    # overflows its candidate lists and the overflow-proof schedule must take over; result still exact
+    # (values are split over two columns so that every stored number is bf16-exact: the bf16 candidate
+    # stage is then exact and the only difficulty is the ordering)
+    n, d = 60000, 64
+    v = np.arange(n) // 4  # ascending scores with 4-way ties
+    base = np.zeros((n, d), np.float32)
+    base[:, 0], base[:, 1] = v // 128, v % 128
+    q = np.zeros((3, d), np.float32)
+    q[:, 0], q[:, 1] = [128, 256, 384], [1, 2, 3]
+    idx = om.FlatIPIndex(d)
+    idx.add(base)
+    D, I = idx.search(q, 100)
+    assert idx.stat("overflow_retries") >= 1
+    D0, I0 = oracle.flat_ip_search(q, base, 100)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+    idx.set_param("force_safe_rounds", 1)
+    D, I = idx.search(q, 100)
+    np.testing.assert_array_equal(I, I0)
+
+
+def _eps_check(q, x, D, I, k, rel=2e-5):
+    """Every returned (id, score) must be a valid top-k answer up to eps-ties: the float64 score of the
+    r-th returned id equals the r-th best float64 score within eps, and the returned fp32 score equals the
+    float64 score of that id within eps.  eps = rel * |q| * |x|_max (fp32 summation-order noise)."""
+    s = q.astype(np.float64) @ x.astype(np.float64).T
+    best = -np.sort(-s, axis=1)[:, :k]
+    eps = rel * np.linalg.norm(q, axis=1, keepdims=True) * np.linalg.norm(x, axis=1).max()
+    got = np.take_along_axis(s, I, axis=1)
+    assert (np.abs(got - best) <= eps).all(), "returned ids are not an eps-valid top-k"
+    assert (np.abs(D - got) <= eps).all(), "returned scores deviate from exact scores"
+    assert (np.diff(D, axis=1) <= 0).all(), "scores not sorted descending"
+    for r in range(I.shape[0]):
+        assert len(set(I[r].tolist())) == k, "duplicate ids"
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(40000, 768, 150, 100), (100000, 768, 64, 1000), (30000, 1024, 33, 10)])
+def test_gaussian_eps_aware(om, n, d, nq, k):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    idx = om.FlatIPIndex(d)
+    idx.add(x)
+    D, I = idx.search(q, k)
+    _eps_check(q, x, D, I, k)
+    # device-resident entry point gives the same answer
+    Dd, Id = idx.search_device(torch.from_numpy(q).cuda(), k)
+    np.testing.assert_array_equal(Id.cpu().numpy(), I)
+
+
+def test_normalized_embeddings(om):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((50000, 768), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((40, 768), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    idx = om.FlatIPIndex(768)
+    idx.add(x)
+    D, I = idx.search(q, 100)
+    _eps_check(q, x, D, I, 100)
+
+
+def test_sharded_merge_matches_unsharded(om):
+    # single-GPU "logical shards": 4 indexes over contiguous row ranges, merged through om_topk_merge
+    rng = np.random.default_rng(2)
+    x, q = _int_data(rng, 8000, 64, -3, 3), _int_data(rng, 21, 64, -3, 3)
+    k = 50
+    Dp, Ip = [], []
+    for s in range(4):
+        idx = om.FlatIPIndex(64)
+        idx.add(x[s * 2000:(s + 1) * 2000])
+        D, I = idx.search_device(torch.from_numpy(q).cuda(), k, id_offset=s * 2000)
+        Dp.append(D); Ip.append(I)
+    D, I = om.merge_topk_device(torch.stack(Dp), torch.stack(Ip), k)
+    D0, I0 = oracle.flat_ip_search(q, x, k)
+    np.testing.assert_array_equal(I.cpu().numpy(), I0)
+    np.testing.assert_array_equal(D.cpu().numpy(), D0)
+    # and against the oracle's own merge
+    D1, I1 = oracle.merge_topk([(a.cpu().numpy(), b.cpu().numpy()) for a, b in zip(Dp, Ip)], k)
+    np.testing.assert_array_equal(I.cpu().numpy(), I1)
+
+
+def test_zero_copy_ingest(om):
+    rng = np.random.default_rng(9)
+    x, q = _int_data(rng, 1500, 128), _int_data(rng, 6, 128)
+    idx = om.FlatIPIndex(128)
+    rows = idx.reserve_rows(1500)
+    rows.copy_(torch.from_numpy(x).cuda())
+    idx.commit_rows(1500)
+    D, I = idx.search(q, 30)
+    D0, I0 = oracle.flat_ip_search(q, x, 30)
+    np.testing.assert_array_equal(I, I0)
