@@ -110,9 +110,12 @@ int om_index_reset(om_index* idx);
 int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
                     om_memkind out_kind, int64_t id_offset, void* stream);
 /* Tunables: "rescore_slack" (extra bf16-stage candidates kept per query; default max(64, k/8)),
- * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing). */
+ * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing),
+ * "profile" (1 = bracket every kernel launch of a search with CUDA events on the launching stream). */
 int om_index_set_param(om_index* idx, const char* name, int64_t value);
-/* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity). */
+/* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity),
+ * "launches" (kernels launched), and with "profile" on: "scan_ns", "select_ns", "finalize_ns" (device time
+ * summed over the launches of each kind). */
 int64_t om_index_get_stat(const om_index* idx, const char* name);
 void om_index_destroy(om_index* idx);
 

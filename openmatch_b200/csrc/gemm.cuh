@@ -41,6 +41,10 @@ struct GemmCfg {
 //   void begin(State&, int row, int m_blk, int n_blk) const;  once per tile
 //   void chunk(State&, int row, int col0, const float (&v)[32]) const;   v = C[row, col0 .. col0+31]
 //   void end(State&, int row) const;                           once per tile
+//   static constexpr bool kPrefetch = false;                   true: prefetch(State&, row, col0) is called for the
+//        thread's first chunk BEFORE waiting on the accumulator, and chunk(..., int next_col0) receives the
+//        column of the thread's next chunk (-1: none) so that global operands (residual) are always one
+//        chunk ahead of the math
 //   static constexpr int kPasses = 1;                          2: the accumulator tile is read twice,
 //        chunk(..., int pass) is called for pass 0 then pass 1 with between(State&, int row) in between
 //        (TMEM re-reads are cheap; used by the search filter to count survivors before appending them)
@@ -156,6 +160,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * kBlockM + ew * 32 + lane;
       typename Epi::State st;
       epi.begin(st, row, m_blk, n_blk);
+      if constexpr (Epi::kPrefetch) epi.prefetch(st, row, n_blk * BN + half * kChunks * 32);  // before the wait
       mbar_wait(&tfull_bar[as], aphase, 4);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16);
@@ -174,6 +179,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if constexpr (Epi::kPasses > 1)
             epi.chunk(st, row, n_blk * BN + c * 32, v, pass);
+          else if constexpr (Epi::kPrefetch)
+            epi.chunk(st, row, n_blk * BN + c * 32, v, c + 1 < (half + 1) * kChunks ? n_blk * BN + (c + 1) * 32 : -1);
           else
             epi.chunk(st, row, n_blk * BN + c * 32, v);
         }
@@ -225,37 +232,59 @@ struct EpiStoreF32 {  // C fp32 = acc (+ bias[n]) (+ resid[m, n])
   float* C;
   int64_t ldc;
   const float* bias;   // nullable, [N]
-  const float* resid;  // nullable, [M, ldr]; may alias C
+  const float* resid;  // nullable, [M, ldr]; may alias C (in-place residual add)
   int64_t ldr;
   int M, N;
   static constexpr int kPasses = 1;
-  struct State {};
+  static constexpr bool kPrefetch = true;
+  struct State {
+    float4 pre[8];  // residual of the chunk about to be processed
+  };
   __device__ __forceinline__ void begin(State&, int, int, int) const {}
   __device__ __forceinline__ void end(State&, int) const {}
-  __device__ __forceinline__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
+  __device__ __forceinline__ bool fast(int row, int col0) const {
+    return row < M && col0 + 32 <= N && (((ldc | ldr) & 3) == 0);
+  }
+  __device__ __forceinline__ void prefetch(State& s, int row, int col0) const {
+    if (resid && col0 >= 0 && fast(row, col0)) {
+      const float4* r = reinterpret_cast<const float4*>(resid + (int64_t)row * ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s.pre[j] = r[j];
+    }
+  }
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int next_col0) const {
     if (row >= M || col0 >= N) return;
     float* out = C + (int64_t)row * ldc + col0;
-    if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    if (fast(row, col0)) {
+      float4 cur[8];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        if (bias) {
-          const float4 b = *reinterpret_cast<const float4*>(bias + col0 + i);
-          o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
-        }
-        if (resid) {
-          const float4 r = *reinterpret_cast<const float4*>(resid + (int64_t)row * ldr + col0 + i);
-          o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
-        }
-        *reinterpret_cast<float4*>(out + i) = o;
+      for (int j = 0; j < 8; ++j) cur[j] = resid ? s.pre[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      // all loads of the NEXT chunk are issued before any store of this one: with resid aliasing C the
+      // compiler must otherwise order every load behind the previous store (one HBM round trip each)
+      prefetch(s, row, next_col0);
+      float4 b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        b[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = v[4 * j] + b[j].x + cur[j].x;
+        o.y = v[4 * j + 1] + b[j].y + cur[j].y;
+        o.z = v[4 * j + 2] + b[j].z + cur[j].z;
+        o.w = v[4 * j + 3] + b[j].w + cur[j].w;
+        reinterpret_cast<float4*>(out)[j] = o;
       }
     } else {
-      for (int i = 0; i < 32 && col0 + i < N; ++i) {
-        float o = v[i];
-        if (bias) o += bias[col0 + i];
-        if (resid) o += resid[(int64_t)row * ldr + col0 + i];
-        out[i] = o;
-      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) {
+          float o = v[i];
+          if (bias) o += bias[col0 + i];
+          if (resid) o += resid[(int64_t)row * ldr + col0 + i];
+          out[i] = o;
+        }
+      prefetch(s, row, next_col0);
     }
   }
 };

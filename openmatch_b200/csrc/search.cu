@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "common.h"
 #include "gemm.cuh"
@@ -78,6 +79,7 @@ struct EpiScan {
   // slots with ONE atomicAdd per (thread, tile) — an append per survivor would stall the warp for a full
   // L2 round trip each time — and pass 1 re-reads TMEM and stores the keys (fire-and-forget stores).
   static constexpr int kPasses = 2;
+  static constexpr bool kPrefetch = false;
   struct State {
     float t;
     int n, pos;
@@ -157,26 +159,88 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* s, int P, 
   }
 }
 
-// SELECT: one CTA per query.  Keeps the best min(cnt, kp) candidates (sorted) at the head of the list and
-// publishes the kp-th score as the new strict threshold.
-__global__ void __launch_bounds__(512) select_kernel(unsigned long long* cand, int* count, float* thr, int C, int kp,
+// SELECT: one CTA per query.  MSB-first radix select (8-bit digits) of the kp-th largest key among the cnt
+// candidates, then compaction of the keys >= it to the head of the list (unordered) and publication of its
+// score as the new strict threshold.  (A full shared-memory sort here costs ~35 GB of smem traffic per
+// round at nq = 6980 — it was 43 % of the search time; selection needs 8 read-only passes.)
+__global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, int* count, float* thr, int C, int kp,
                                                      int cnt_override) {
   extern __shared__ unsigned long long skeys[];
-  const int q = blockIdx.x;
+  __shared__ int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_out;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   unsigned long long* mine = cand + static_cast<size_t>(q) * C;
   int cnt = cnt_override >= 0 ? cnt_override : count[q];
   cnt = cnt < C ? cnt : C;
-  int P = 1;
-  while (P < cnt) P <<= 1;
-  if (P < 2) P = 2;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < cnt ? mine[i] : 0ull;
+  if (cnt <= kp) {  // nothing to drop yet: no threshold
+    if (tid == 0) {
+      count[q] = cnt;
+      thr[q] = __int_as_float(0xff800000);
+    }
+    return;
+  }
+  for (int i = tid; i < cnt; i += blockDim.x) skeys[i] = mine[i];
+  if (tid == 0) {
+    s_prefix = 0ull;
+    s_remaining = kp;
+    s_out = 0;
+  }
   __syncthreads();
-  bitonic_sort_desc(skeys, P, threadIdx.x, blockDim.x);
-  const int keep = cnt < kp ? cnt : kp;
-  for (int i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = skeys[i];
-  if (threadIdx.x == 0) {
-    count[q] = keep;
-    thr[q] = cnt >= kp ? key_score(skeys[kp - 1]) : __int_as_float(0xff800000);
+  unsigned long long mask = 0ull;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
+      const int i = i0 + tid;
+      const bool live = i < cnt && (skeys[i] & mask) == prefix;
+      const int digit = live ? static_cast<int>((skeys[i] >> shift) & 255ull) : -1;
+      // warp-aggregate equal digits (top bytes of similar scores collide heavily)
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (live && lane == (__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns digits 255-8l .. 248-8l (descending); find the digit where the running count from the
+      // top reaches `remaining`
+      int local[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        local[j] = hist[255 - (lane * 8 + j)];
+        sum += local[j];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int excl = incl - sum, remaining = s_remaining;
+      __syncwarp();
+      if (excl < remaining && remaining <= incl) {  // exactly one lane
+        int run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < remaining && remaining <= run + local[j]) {
+            s_prefix = prefix | (static_cast<unsigned long long>(255 - (lane * 8 + j)) << shift);
+            s_remaining = remaining - run;
+          }
+          run += local[j];
+        }
+      }
+    }
+    mask |= 255ull << shift;
+    __syncthreads();
+  }
+  const unsigned long long kth = s_prefix;  // keys are unique, so exactly kp keys are >= kth
+  for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
+    const int i = i0 + tid;
+    if (i < cnt && skeys[i] >= kth) mine[atomicAdd(&s_out, 1)] = skeys[i];
+  }
+  if (tid == 0) {
+    count[q] = kp;
+    thr[q] = key_score(kth);
   }
 }
 
@@ -307,7 +371,13 @@ struct om_index {
   __nv_bfloat16* xb = nullptr;
   int64_t rescore_slack = -1;
   int force_safe = 0;
-  int64_t st_rounds = 0, st_retries = 0, st_capacity = 0;
+  int64_t st_rounds = 0, st_retries = 0, st_capacity = 0, st_launches = 0;
+  // optional per-phase device timing (CUDA events on the launching stream), enabled by set_param("profile", 1)
+  int profile = 0;
+  double st_scan_us = 0, st_select_us = 0, st_final_us = 0;
+  std::vector<cudaEvent_t> ev;  // pool: [2i] start, [2i+1] stop
+  std::vector<int> ev_kind;     // 0 scan, 1 select, 2 finalize
+  size_t ev_used = 0;
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -372,6 +442,7 @@ void om_index_destroy(om_index* ix) {
   cudaFree(ix->xf);
   cudaFree(ix->xb);
   cudaFree(ix->ws);
+  for (cudaEvent_t e : ix->ev) cudaEventDestroy(e);
   delete ix;
 }
 
@@ -445,6 +516,8 @@ int om_index_set_param(om_index* ix, const char* name, int64_t value) {
     ix->rescore_slack = value;
   } else if (!strcmp(name, "force_safe_rounds")) {
     ix->force_safe = value != 0;
+  } else if (!strcmp(name, "profile")) {
+    ix->profile = value != 0;
   } else {
     return fail(OM_EINVAL, "om_index_set_param: unknown parameter '%s'", name);
   }
@@ -456,12 +529,53 @@ int64_t om_index_get_stat(const om_index* ix, const char* name) {
   if (!strcmp(name, "rounds")) return ix->st_rounds;
   if (!strcmp(name, "overflow_retries")) return ix->st_retries;
   if (!strcmp(name, "candidates")) return ix->st_capacity;
+  if (!strcmp(name, "launches")) return ix->st_launches;
+  if (!strcmp(name, "scan_ns")) return static_cast<int64_t>(ix->st_scan_us * 1e3);
+  if (!strcmp(name, "select_ns")) return static_cast<int64_t>(ix->st_select_us * 1e3);
+  if (!strcmp(name, "finalize_ns")) return static_cast<int64_t>(ix->st_final_us * 1e3);
   return -1;
 }
 
 }  // extern "C"
 
 namespace {
+
+// profiling helpers: bracket a launch with events from the index's pool
+struct Timed {
+  om_index* ix;
+  cudaStream_t st;
+  bool on;
+  Timed(om_index* ix_, cudaStream_t st_, int kind) : ix(ix_), st(st_), on(ix_->profile != 0) {
+    if (!on) return;
+    if (ix->ev_used + 2 > ix->ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+        on = false;
+        return;
+      }
+      ix->ev.push_back(a);
+      ix->ev.push_back(b);
+      ix->ev_kind.push_back(0);
+    }
+    ix->ev_kind[ix->ev_used / 2] = kind;
+    cudaEventRecord(ix->ev[ix->ev_used], st);
+  }
+  ~Timed() {
+    if (!on) return;
+    cudaEventRecord(ix->ev[ix->ev_used + 1], st);
+    ix->ev_used += 2;
+  }
+};
+
+void collect_profile(om_index* ix) {
+  for (size_t i = 0; i + 1 < ix->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ix->ev[i], ix->ev[i + 1]) != cudaSuccess) continue;
+    const int kind = ix->ev_kind[i / 2];
+    (kind == 0 ? ix->st_scan_us : kind == 1 ? ix->st_select_us : ix->st_final_us) += ms * 1e3;
+  }
+  ix->ev_used = 0;
+}
 
 struct ChunkWs {
   unsigned long long* cand;
@@ -502,11 +616,18 @@ int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, const Ch
     epi.C = C;
     epi.row_base = static_cast<uint32_t>(pos);
     epi.dense = first ? 1 : 0;
-    cudaError_t e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, ix->xb + static_cast<size_t>(pos) * ix->dpad, ix->dpad,
-                                              nq, static_cast<int>(step), ix->d, epi, sms, st);
-    if (e != cudaSuccess) return fail(OM_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
-    select_kernel<<<nq, 512, sel_smem, st>>>(w.cand, w.count, w.thr, C, kp, first ? static_cast<int>(step) : -1);
+    {
+      Timed t(ix, st, 0);
+      cudaError_t e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, ix->xb + static_cast<size_t>(pos) * ix->dpad,
+                                                ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st);
+      if (e != cudaSuccess) return fail(OM_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    {
+      Timed t(ix, st, 1);
+      select_kernel<<<nq, 256, sel_smem, st>>>(w.cand, w.count, w.thr, C, kp, first ? static_cast<int>(step) : -1);
+    }
     OM_CUDA(cudaGetLastError());
+    ix->st_launches += 2;
     pos += step;
     first = false;
     ix->st_rounds++;
@@ -535,6 +656,9 @@ extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, i
   ix->st_capacity = C;
   ix->st_rounds = 0;
   ix->st_retries = 0;
+  ix->st_launches = 1;  // the query fp32 -> bf16 conversion below
+  ix->st_scan_us = ix->st_select_us = ix->st_final_us = 0;
+  ix->ev_used = 0;
 
   const int QCHUNK = 16384;
   const int nqc_max = std::min(nq, QCHUNK);
@@ -587,10 +711,14 @@ extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, i
       } else {
         OM_TRY(sweep(ix, qb + static_cast<size_t>(q0) * dpad, nqc, kp, C, w, safe, sms, st));
       }
-      finalize_kernel<<<nqc, 256, fin_smem, st>>>(w.cand, w.count, C, qf + static_cast<size_t>(q0) * d, ix->xf, d, k,
-                                                  dD + static_cast<size_t>(q0) * k, dI + static_cast<size_t>(q0) * k,
-                                                  id_offset);
+      {
+        Timed t(ix, st, 2);
+        finalize_kernel<<<nqc, 256, fin_smem, st>>>(w.cand, w.count, C, qf + static_cast<size_t>(q0) * d, ix->xf, d, k,
+                                                    dD + static_cast<size_t>(q0) * k, dI + static_cast<size_t>(q0) * k,
+                                                    id_offset);
+      }
       OM_CUDA(cudaGetLastError());
+      ix->st_launches += 1;
       int ovf = 0;
       if (ix->n > 0) {
         OM_CUDA(cudaMemcpyAsync(&ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -609,6 +737,7 @@ extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, i
     OM_CUDA(cudaMemcpyAsync(I, dI, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
   }
   OM_CUDA(cudaStreamSynchronize(st));
+  if (ix->profile) collect_profile(ix);
   return 0;
 }
 

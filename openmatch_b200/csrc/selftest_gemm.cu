@@ -33,6 +33,7 @@ struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics 
   float thr;
   int M, N;
   static constexpr int kPasses = 1;
+  static constexpr bool kPrefetch = false;
   struct State {
     int cnt;
   };

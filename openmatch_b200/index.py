@@ -140,6 +140,31 @@ def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor, k: int) -> T
     return D, I
 
 
+def exchange_and_merge(D_local: torch.Tensor, I_local: torch.Tensor, k: int, group=None, merge=None):
+    """Exchange step of the row-sharded search: all-gather the per-shard [nq, k] (score, global id) lists in
+    rank order (NCCL over NVLink on GPUs) and merge them by (score desc, id asc) on every rank.  ``merge``
+    defaults to the CUDA merge kernel; tests inject the oracle's merge to run this on CPU / gloo."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return D_local, I_local
+    Dp = torch.empty((world,) + tuple(D_local.shape), dtype=D_local.dtype, device=D_local.device)
+    Ip = torch.empty((world,) + tuple(I_local.shape), dtype=I_local.dtype, device=I_local.device)
+    dist.all_gather(list(Dp.unbind(0)), D_local.contiguous(), group=group)  # views of one [W, nq, k] buffer
+    dist.all_gather(list(Ip.unbind(0)), I_local.contiguous(), group=group)
+    return (merge or merge_topk_device)(Dp, Ip, k)
+
+
+def shard_offsets(n_local: int, group=None):
+    """(global id of this rank's first row, total rows) for rank-major contiguous shards."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0, n_local
+    counts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(counts, int(n_local), group=group)
+    return sum(counts[: dist.get_rank(group)]), sum(counts)
+
+
 class ShardedFlatIPIndex:
     """Row-sharded index: rank r of ``torch.distributed`` holds rows [offset_r, offset_r + n_r) in its own
     HBM.  ``search`` = replicate queries -> local fused scan/top-k with global ids -> all-gather of the
@@ -161,15 +186,7 @@ class ShardedFlatIPIndex:
 
     def finalize_offsets(self) -> None:
         """Call once after all ranks added their rows: computes global id offsets (rank-major)."""
-        n_local = torch.tensor([self.local.ntotal], dtype=torch.int64, device="cuda")
-        if self.world > 1:
-            all_n = [torch.zeros_like(n_local) for _ in range(self.world)]
-            self.dist.all_gather(all_n, n_local, group=self.group)
-            counts = [int(t.item()) for t in all_n]
-        else:
-            counts = [int(n_local.item())]
-        self.offset = sum(counts[: self.rank])
-        self._ntotal = sum(counts)
+        self.offset, self._ntotal = shard_offsets(self.local.ntotal, self.group)
 
     @property
     def ntotal(self) -> int:
@@ -177,13 +194,7 @@ class ShardedFlatIPIndex:
 
     def search_device(self, q: torch.Tensor, k: int):
         Dl, Il = self.local.search_device(q, k, id_offset=self.offset)
-        if self.world == 1:
-            return Dl, Il
-        Dp = torch.empty((self.world,) + tuple(Dl.shape), dtype=Dl.dtype, device=Dl.device)
-        Ip = torch.empty((self.world,) + tuple(Il.shape), dtype=Il.dtype, device=Il.device)
-        self.dist.all_gather_into_tensor(Dp, Dl, group=self.group)
-        self.dist.all_gather_into_tensor(Ip, Il, group=self.group)
-        return merge_topk_device(Dp, Ip, k)
+        return exchange_and_merge(Dl, Il, k, self.group)
 
     def search(self, q, k: int):
         if not isinstance(q, torch.Tensor):

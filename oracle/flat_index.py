@@ -21,28 +21,46 @@ import numpy as np
 NEG_FILL = np.float32(-3.4028234663852886e38)  # std::numeric_limits<float>::lowest()
 
 
+def _topk_row_exact(s: np.ndarray, kk: int) -> np.ndarray:
+    """Column indices of the kk largest entries of one row, ordered by (score desc, column asc)."""
+    n = s.shape[0]
+    if kk < n:
+        part = np.argpartition(-s, kk - 1)[:kk]
+        kth = s[part].min()
+        gt = np.flatnonzero(s > kth)
+        eq = np.flatnonzero(s == kth)[: kk - gt.size]  # ascending column = ascending row id
+        idx = np.concatenate([gt, eq])
+    else:
+        idx = np.arange(n)
+    return idx[np.lexsort((idx, -s[idx].astype(np.float64)))]
+
+
 def _topk_rows(scores: np.ndarray, k: int, row_offset: int = 0):
-    """Top-k of every row of ``scores`` ordered by (score desc, column asc).  Returns (D f32, I i64)."""
+    """Top-k of every row of ``scores`` ordered by (score desc, column asc).  Returns (D f32, I i64).
+
+    Fast path: multi-threaded ``torch.topk`` for the selection, then a stable re-sort for the tie order; rows
+    whose k-th score is tied with an unselected column fall back to the exact per-row routine."""
+    import torch
     nq, n = scores.shape
     kk = min(k, n)
     D = np.full((nq, k), NEG_FILL, dtype=np.float32)
     I = np.full((nq, k), -1, dtype=np.int64)
     if kk == 0:
         return D, I
-    for r in range(nq):
-        s = scores[r]
-        if kk < n:
-            part = np.argpartition(-s, kk - 1)[:kk]
-            kth = s[part].min()
-            gt = np.flatnonzero(s > kth)
-            eq = np.flatnonzero(s == kth)[: kk - gt.size]  # ascending column = ascending row id
-            idx = np.concatenate([gt, eq])
-        else:
-            idx = np.arange(n)
-        order = np.lexsort((idx, -s[idx].astype(np.float64)))
-        idx = idx[order]
-        D[r, :kk] = s[idx]
-        I[r, :kk] = idx + row_offset
+    st = torch.from_numpy(np.ascontiguousarray(scores))
+    vals, idx = torch.topk(st, kk, dim=1, sorted=True)
+    vals, idx = vals.numpy(), idx.numpy()
+    by_col = np.argsort(idx, axis=1, kind="stable")
+    idx, vals = np.take_along_axis(idx, by_col, 1), np.take_along_axis(vals, by_col, 1)
+    by_score = np.argsort(-vals.astype(np.float64), axis=1, kind="stable")
+    idx, vals = np.take_along_axis(idx, by_score, 1), np.take_along_axis(vals, by_score, 1)
+    if kk < n:
+        n_ge = (st >= torch.from_numpy(vals[:, -1:].copy())).sum(dim=1).numpy()
+        for r in np.flatnonzero(n_ge > kk):  # boundary ties: which equal-score columns survive matters
+            sel = _topk_row_exact(scores[r], kk)
+            idx[r], vals[r] = sel, scores[r][sel]
+    D[:, :kk] = vals
+    I[:, :kk] = idx + row_offset
     return D, I
 
 
