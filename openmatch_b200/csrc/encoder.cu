@@ -266,8 +266,11 @@ struct AttnParams {
   __nv_bfloat16* ctx;             // [T, I]
 };
 
-constexpr int kAttnSmemQ = 0, kAttnSmemK = 16384, kAttnSmemV = 32768, kAttnSmemP = 49152;
-constexpr int kAttnSmemMisc = 49152 + 32768;  // kb[128] f32, rel[256] f32, barriers, tmem slot
+// P (32 KB) overwrites the Q and K tiles, which are dead once S = Q K^T has completed; O overwrites the first
+// 64 TMEM columns of S, dead once the softmax has read it: 52 KB smem + 128 TMEM columns per CTA -> 4 CTAs/SM.
+constexpr int kAttnSmemQ = 0, kAttnSmemK = 16384, kAttnSmemV = 32768, kAttnSmemP = 0;
+constexpr int kAttnSmemMisc = 49152;  // kb[128] f32, rel[256] f32, barriers, tmem slot
+constexpr int kAttnTmemCols = 128;
 constexpr int kAttnSmemBytes = kAttnSmemMisc + 512 + 1024 + 64 + 1024;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -276,7 +279,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 4)
 attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt, AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -298,7 +301,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, kAttnTmemCols);
     tmem_relinquish();
   }
   {
@@ -398,7 +401,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
     const uint32_t pa = smem_u32(sP), va = smem_u32(smem + kAttnSmemV);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      umma_bf16_ss(tmem_base + 128, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, kDescKMajorSW128),
+      umma_bf16_ss(tmem_base, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, kDescKMajorSW128),
                    umma_smem_desc(va + (k >> 2) * 8192 + (k & 3) * 32, kDescKMajorSW128), idesc_o, k != 0 ? 1u : 0u);
     umma_commit(&bars[2]);
   }
@@ -407,7 +410,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
 #pragma unroll 1
   for (int c2 = 0; c2 < 2; ++c2) {
     uint32_t raw[32];
-    tmem_ld_32x32b_x32(taddr + 128 + c2 * 32, raw);
+    tmem_ld_32x32b_x32(taddr + c2 * 32, raw);
     tmem_ld_wait();
     if (row_valid) {
       uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<int64_t>(row0 + r) * p.I + head * kHeadDim + c2 * 32);
@@ -425,7 +428,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
   __syncthreads();
   if (warp == 0) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, kAttnTmemCols);
   }
 }
 

@@ -169,18 +169,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (Epi::kPasses > 1) {
           if (pass > 0) epi.between(st, row);
         }
-#pragma unroll 1
-        for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
+        // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
+        uint32_t rbuf[2][32];
+        const int c0 = half * kChunks;
+        tmem_ld_32x32b_x32(taddr + c0 * 32, rbuf[0]);
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int c = c0 + ci;
           tmem_ld_wait();
+          if (ci + 1 < kChunks) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(ci + 1) & 1]);
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rbuf[ci & 1][i]);
           if constexpr (Epi::kPasses > 1)
             epi.chunk(st, row, n_blk * BN + c * 32, v, pass);
           else if constexpr (Epi::kPrefetch)
-            epi.chunk(st, row, n_blk * BN + c * 32, v, c + 1 < (half + 1) * kChunks ? n_blk * BN + (c + 1) * 32 : -1);
+            epi.chunk(st, row, n_blk * BN + c * 32, v, ci + 1 < kChunks ? n_blk * BN + (c + 1) * 32 : -1);
           else
             epi.chunk(st, row, n_blk * BN + c * 32, v);
         }

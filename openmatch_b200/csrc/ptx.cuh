@@ -71,8 +71,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t site) {
+  // try_wait suspends the thread in hardware until the phase completes or a time limit expires, so this
+  // loop is not a busy spin.  The fault word (a global load, ~1 us) and the clock are consulted only every
+  // 1024 wake-ups: polling them on every iteration added a DRAM round trip to every pipeline hand-off.
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) != 0) continue;
     if (*reinterpret_cast<volatile unsigned int*>(&om_dev_fault) != 0u) return;
     if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {
       atomicCAS(&om_dev_fault, 0u, (site << 16) | (blockIdx.x & 0xffffu) | 0x80000000u);
@@ -82,6 +87,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
 }
 // Bounded wait on phase `parity`. `site` identifies the call site in the fault word.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site) {
+  if (mbar_try_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, site);
 }

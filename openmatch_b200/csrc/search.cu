@@ -11,7 +11,7 @@
 //             scores never leave TMEM/registers; a thread owns one query row, compares its 32-column chunk
 //             against that query's running threshold and appends the rare survivors
 //             (key = orderable(score) << 32 | ~row) to the query's candidate list in HBM.
-//             The corpus is swept in rounds of doubling size; after each round
+//             The corpus is swept in rounds of geometrically growing size; after each round
 //   2. SELECT a per-query bitonic sort in shared memory keeps the best kp = k + slack candidates and
 //             publishes the kp-th score as the next round's (strict) threshold.  Expected survivors per
 //             round ~ kp, so the list capacity C >= 2.5 kp + 512 is ample for exchangeable data; an overflow (e.g.
@@ -371,6 +371,7 @@ struct om_index {
   __nv_bfloat16* xb = nullptr;
   int64_t rescore_slack = -1;
   int force_safe = 0;
+  int growth = 4;  // each round scans (growth - 1) x the rows seen so far
   int64_t st_rounds = 0, st_retries = 0, st_capacity = 0, st_launches = 0;
   // optional per-phase device timing (CUDA events on the launching stream), enabled by set_param("profile", 1)
   int profile = 0;
@@ -516,6 +517,9 @@ int om_index_set_param(om_index* ix, const char* name, int64_t value) {
     ix->rescore_slack = value;
   } else if (!strcmp(name, "force_safe_rounds")) {
     ix->force_safe = value != 0;
+  } else if (!strcmp(name, "round_growth")) {
+    if (value < 2 || value > 8) return fail(OM_EINVAL, "round_growth must be in [2, 8]");
+    ix->growth = static_cast<int>(value);
   } else if (!strcmp(name, "profile")) {
     ix->profile = value != 0;
   } else {
@@ -586,8 +590,9 @@ struct ChunkWs {
 
 // One sweep of the corpus for a chunk of queries.  safe=false: doubling rounds; safe=true: fixed rounds of
 // C - kp rows, which cannot overflow.
-int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, const ChunkWs& w, bool safe, int sms,
-          cudaStream_t st) {
+int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, int growth_, const ChunkWs& w, bool safe,
+          int sms, cudaStream_t st) {
+  const int64_t growth = growth_;
   const int64_t N = ix->n;
   OM_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(int), st));
   int64_t pos = 0;
@@ -605,7 +610,7 @@ int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, const Ch
     else if (safe)
       step = std::min<int64_t>(N - pos, std::max<int64_t>(256, ((C - kp) / 256) * 256));
     else
-      step = std::min<int64_t>(N - pos, pos);
+      step = std::min<int64_t>(N - pos, (growth - 1) * pos);
     EpiScan epi;
     epi.thr = w.thr;
     epi.cand = w.cand;
@@ -650,9 +655,15 @@ extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, i
   const int64_t kp64 = std::min<int64_t>(static_cast<int64_t>(k) + slack, std::max<int64_t>(ix->n, 1));
   if (kp64 > 4096) return fail(OM_EINVAL, "om_index_search: k + slack = %lld exceeds 4096", (long long)kp64);
   const int kp = static_cast<int>(kp64);
-  // Expected list length after a doubling round is ~2 kp (kp kept + ~kp new survivors, sd ~ sqrt(2 kp)).
-  int C = 1024;
-  while (C < (5 * kp) / 2 + 512) C <<= 1;
+  // Expected list length after a round that multiplies the rows seen by g is ~g kp (kp kept + ~(g-1) kp new
+  // survivors); 25 % + 512 entries of head-room cover its spread for exchangeable row order.
+  int growth = ix->growth, C = 0;
+  for (;; --growth) {  // large k: fall back to a slower-growing schedule that fits the 16384-entry select
+    C = 1024;
+    while (C < (5 * growth * kp) / 4 + 512) C <<= 1;
+    if (C <= 16384 || growth == 2) break;
+  }
+  if (C > 16384) return fail(OM_EINVAL, "om_index_search: candidate list of %d entries exceeds 16384; lower k", C);
   ix->st_capacity = C;
   ix->st_rounds = 0;
   ix->st_retries = 0;
@@ -709,7 +720,7 @@ extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, i
         fill_i32<<<(nqc + 255) / 256, 256, 0, st>>>(w.count, 0, nqc);
         OM_CUDA(cudaGetLastError());
       } else {
-        OM_TRY(sweep(ix, qb + static_cast<size_t>(q0) * dpad, nqc, kp, C, w, safe, sms, st));
+        OM_TRY(sweep(ix, qb + static_cast<size_t>(q0) * dpad, nqc, kp, C, growth, w, safe, sms, st));
       }
       {
         Timed t(ix, st, 2);

@@ -115,7 +115,7 @@ def _ids(gen, B, L, vocab, ragged=True):
     ids = torch.randint(5, vocab, (B, L), generator=gen)
     mask = torch.ones(B, L, dtype=torch.long)
     if ragged:
-        lens = torch.randint(2, L + 1, (B,), generator=gen)
+        lens = torch.randint(min(2, L), L + 1, (B,), generator=gen)
         lens[0] = L
         for b in range(B):
             mask[b, lens[b]:] = 0
