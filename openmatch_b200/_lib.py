@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libopenmatch_b200.so")
+LIB_PATH = os.environ.get("OPENMATCH_B200_LIB") or os.path.join(_HERE, "lib", "libopenmatch_b200.so")
 
 OM_F32, OM_BF16, OM_F16 = 0, 1, 2
 OM_HOST, OM_DEVICE = 0, 1

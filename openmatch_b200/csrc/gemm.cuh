@@ -27,13 +27,13 @@ constexpr int kGemmProducerThreads = 128;  // warps 0..3: TMA, MMA, TMEM alloc, 
 
 template <int BN, int STAGES>
 struct GemmCfg {
-  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
+  static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "BN must be 64, 128, 192 or 256");
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
+  static constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // power of two >= 2 * BN
 };
 
 // Epilogue functor contract (all methods __device__, called by the epilogue threads; thread <-> row (half)):
@@ -45,6 +45,10 @@ struct GemmCfg {
 //        thread's first chunk BEFORE waiting on the accumulator, and chunk(..., int next_col0) receives the
 //        column of the thread's next chunk (-1: none) so that global operands (residual) are always one
 //        chunk ahead of the math
+//   static constexpr int kSmemBytes = 0;                       > 0: that much dynamic smem is reserved for the functor
+//        and handed over through bind(State&, uint8_t* smem, int epilogue_thread_index) before begin()
+//   end() runs AFTER the thread's warp has released the accumulator buffer: long-latency tails (atomics,
+//        global stores) placed there overlap the next tile's MMAs
 //   static constexpr int kPasses = 1;                          2: the accumulator tile is read twice,
 //        chunk(..., int pass) is called for pass 0 then pass 1 with between(State&, int row) in between
 //        (TMEM re-reads are cheap; used by the search filter to count survivors before appending them)
@@ -62,6 +66,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_smem = smem + Cfg::kBarOffset + 256;  // Epi::kSmemBytes of scratch owned by the epilogue functor
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
@@ -151,6 +156,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS must be 4 or 8");
     const int ew = (warp - 4) & 3;      // == warp % 4: the TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;   // column half owned by this warp when EPI_WARPS == 8
+    static_assert((BN / 32) % (EPI_WARPS / 4) == 0, "column chunks must split evenly over the epilogue warps");
     constexpr int kChunks = BN / 32 / (EPI_WARPS / 4);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -159,9 +165,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int row = m_blk * kBlockM + ew * 32 + lane;
       typename Epi::State st;
+      if constexpr (Epi::kSmemBytes > 0) epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
       epi.begin(st, row, m_blk, n_blk);
       if constexpr (Epi::kPrefetch) epi.prefetch(st, row, n_blk * BN + half * kChunks * 32);  // before the wait
-      mbar_wait(&tfull_bar[as], aphase, 4);
+      mbar_wait_warp(&tfull_bar[as], aphase, 4);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
@@ -169,24 +176,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (Epi::kPasses > 1) {
           if (pass > 0) epi.between(st, row);
         }
-        // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed
-        uint32_t rbuf[2][32];
+        // Software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed.  The
+        // loop stays ROLLED over chunk pairs (two register buffers): fully unrolling it made the scan kernel
+        // 30 K SASS instructions and instruction-fetch bound (2.3x slower).
         const int c0 = half * kChunks;
-        tmem_ld_32x32b_x32(taddr + c0 * 32, rbuf[0]);
-#pragma unroll
-        for (int ci = 0; ci < kChunks; ++ci) {
-          const int c = c0 + ci;
-          tmem_ld_wait();
-          if (ci + 1 < kChunks) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(ci + 1) & 1]);
+        auto run = [&](const uint32_t (&rb)[32], int c, bool has_next) {
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rbuf[ci & 1][i]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
           if constexpr (Epi::kPasses > 1)
             epi.chunk(st, row, n_blk * BN + c * 32, v, pass);
           else if constexpr (Epi::kPrefetch)
-            epi.chunk(st, row, n_blk * BN + c * 32, v, ci + 1 < kChunks ? n_blk * BN + (c + 1) * 32 : -1);
+            epi.chunk(st, row, n_blk * BN + c * 32, v, has_next ? n_blk * BN + (c + 1) * 32 : -1);
           else
             epi.chunk(st, row, n_blk * BN + c * 32, v);
+        };
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(taddr + c0 * 32, ra);
+        if constexpr (kChunks == 1) {
+          tmem_ld_wait();
+          run(ra, c0, false);
+        } else {
+#pragma unroll 1
+          for (int c = c0; c + 1 < c0 + kChunks; c += 2) {
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rb);
+            run(ra, c, true);
+            tmem_ld_wait();
+            const bool more = c + 2 < c0 + kChunks;
+            if (more) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
+            run(rb, c + 1, more);
+          }
+          if constexpr (kChunks % 2 == 1) {  // odd tail (e.g. BN = 192 with 8 epilogue warps: 3 chunks each)
+            tmem_ld_wait();
+            run(ra, c0 + kChunks - 1, false);
+          }
         }
       }
       tc_fence_before_sync();
@@ -219,13 +243,15 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
   auto kern = gemm_bf16_tn_kernel<BN, STAGES, M_FASTEST, EPI_WARPS, Epi>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes + Epi::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  kern<<<grid, kGemmProducerThreads + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(tmA, tmB, M, N, K, epi);
+  kern<<<grid, kGemmProducerThreads + 32 * EPI_WARPS, Cfg::kSmemBytes + Epi::kSmemBytes, stream>>>(tmA, tmB, M, N, K,
+                                                                                                     epi);
   return cudaGetLastError();
 }
 
@@ -241,6 +267,7 @@ struct EpiStoreF32 {  // C fp32 = acc (+ bias[n]) (+ resid[m, n])
   int M, N;
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = true;
+  static constexpr int kSmemBytes = 0;
   struct State {
     float4 pre[8];  // residual of the chunk about to be processed
   };

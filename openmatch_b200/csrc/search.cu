@@ -67,6 +67,7 @@ __host__ __device__ __forceinline__ float key_score(unsigned long long k) {
 // ---------------------------------------------------------------------------------------------------
 // fused scan epilogue
 // ---------------------------------------------------------------------------------------------------
+template <bool DENSE>
 struct EpiScan {
   const float* thr;          // [nq] strict lower bound per query
   unsigned long long* cand;  // [nq, C]
@@ -74,33 +75,47 @@ struct EpiScan {
   int* overflow;             // single flag
   int nq, n_cols, C;
   uint32_t row_base;  // corpus row of column 0 of this round
-  int dense;          // 1: first round, every score is stored at position = column
-  // Two passes over the accumulator tile: pass 0 counts this thread's survivors, between() reserves their
-  // slots with ONE atomicAdd per (thread, tile) — an append per survivor would stall the warp for a full
-  // L2 round trip each time — and pass 1 re-reads TMEM and stores the keys (fire-and-forget stores).
-  static constexpr int kPasses = 2;
+  // DENSE: first round, every score is stored at position = column (no threshold yet)
+  // One pass over the accumulator tile.  A thread compares its 32-column chunks against its query's
+  // threshold and parks the rare survivors in a private shared-memory stash; the accumulator buffer is then
+  // released to the MMA warp, and only afterwards (end()) does the thread reserve slots in the query's
+  // candidate list with ONE atomicAdd and copy the stash out.  The L2 round trip of the atomic therefore
+  // overlaps the next tile's MMAs instead of holding a TMEM buffer (measured: the MMA warp was waiting for
+  // the epilogue on every tile when the append happened before the release).
+  static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
+  static constexpr int kStash = 12;                     // survivors a thread can park per tile
+  static constexpr int kEpiThreads = 256;               // 8 epilogue warps
+  static constexpr int kSmemBytes = kStash * kEpiThreads * 8;
   struct State {
     float t;
-    int n, pos;
+    int k, tid;
+    unsigned long long* stash;  // [kStash][kEpiThreads], this thread owns column `tid`
   };
+  __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const {
+    s.stash = reinterpret_cast<unsigned long long*>(smem);
+    s.tid = epi_tid;
+  }
   __device__ __forceinline__ void begin(State& s, int row, int, int) const {
-    s.t = (row < nq && !dense) ? thr[row] : __int_as_float(0x7f800000);
-    s.n = 0;
-    s.pos = 0;
+    s.t = (row < nq && !DENSE) ? thr[row] : __int_as_float(0x7f800000);
+    s.k = 0;
   }
-  __device__ __forceinline__ void end(State&, int) const {}
-  __device__ __forceinline__ void between(State& s, int row) const {
-    if (s.n > 0) {
-      s.pos = atomicAdd(count + row, s.n);
-      if (s.pos + s.n > C) *overflow = 1;
-    }
-  }
-  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int pass) const {
-    if (row >= nq || col0 >= n_cols) return;
+  __device__ __noinline__ void flush(State& s, int row) const {
+    const int n = s.k;
+    const int pos = atomicAdd(count + row, n);
     unsigned long long* mine = cand + static_cast<size_t>(row) * C;
-    if (dense) {
-      if (pass != 0) return;
+    for (int j = 0; j < n; ++j)
+      if (pos + j < C) mine[pos + j] = s.stash[j * kEpiThreads + s.tid];
+    if (pos + n > C) *overflow = 1;
+    s.k = 0;
+  }
+  __device__ __forceinline__ void end(State& s, int row) const {
+    if (s.k > 0) flush(s, row);
+  }
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
+    if (row >= nq || col0 >= n_cols) return;
+    if constexpr (DENSE) {
+      unsigned long long* mine = cand + static_cast<size_t>(row) * C;
       if (col0 + 32 <= n_cols) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -118,22 +133,17 @@ struct EpiScan {
     }
     const float t = s.t;
     const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
-    if (pass == 0) {
-      int n = 0;
+    float mx = v[0];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) n += (v[i] > t && i < lim) ? 1 : 0;
-      s.n += n;
-    } else {
-      if (s.n == 0) return;
-      int pos = s.pos;
+    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+    if (!(mx > t)) return;  // common case: nothing in this chunk beats the threshold
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (v[i] > t && i < lim) {
-          if (pos < C) mine[pos] = make_key(v[i], row_base + col0 + i);
-          ++pos;
-        }
+    for (int i = 0; i < 32; ++i) {
+      if (v[i] > t && i < lim) {
+        if (s.k == kStash) flush(s, row);  // dense early rounds: spill while still holding the accumulator
+        s.stash[s.k * kEpiThreads + s.tid] = make_key(v[i], row_base + col0 + i);
+        ++s.k;
       }
-      s.pos = pos;
     }
   }
 };
@@ -611,20 +621,17 @@ int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, int grow
       step = std::min<int64_t>(N - pos, std::max<int64_t>(256, ((C - kp) / 256) * 256));
     else
       step = std::min<int64_t>(N - pos, (growth - 1) * pos);
-    EpiScan epi;
-    epi.thr = w.thr;
-    epi.cand = w.cand;
-    epi.count = w.count;
-    epi.overflow = w.overflow;
-    epi.nq = nq;
-    epi.n_cols = static_cast<int>(step);
-    epi.C = C;
-    epi.row_base = static_cast<uint32_t>(pos);
-    epi.dense = first ? 1 : 0;
     {
       Timed t(ix, st, 0);
-      cudaError_t e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, ix->xb + static_cast<size_t>(pos) * ix->dpad,
-                                                ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st);
+      const __nv_bfloat16* xrows = ix->xb + static_cast<size_t>(pos) * ix->dpad;
+      cudaError_t e;
+      if (first) {
+        EpiScan<true> epi{w.thr, w.cand, w.count, w.overflow, nq, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
+        e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st);
+      } else {
+        EpiScan<false> epi{w.thr, w.cand, w.count, w.overflow, nq, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
+        e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st);
+      }
       if (e != cudaSuccess) return fail(OM_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
     }
     {

@@ -34,6 +34,7 @@ struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics 
   int M, N;
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
+  static constexpr int kSmemBytes = 0;
   struct State {
     int cnt;
   };
@@ -175,6 +176,8 @@ int main(int argc, char** argv) {
   fails += check_case<256, 4, false>(2048, 2304, 768, sms, dump_dir);  // many tiles per CTA
   fails += check_case<256, 4, false, 8>(2048, 2304, 768, sms, dump_dir);  // 8 epilogue warps
   fails += check_case<64, 4, false, 8>(300, 200, 128, sms, dump_dir);
+  fails += check_case<192, 5, false, 8>(1000, 768, 768, sms, dump_dir);  // 192-wide tiles, odd chunk tail
+  fails += check_case<192, 5, false, 4>(300, 500, 192, sms, dump_dir);
   if (fails) {
     printf("SELFTEST FAILED (%d cases)\n", fails);
     return 1;
@@ -183,6 +186,7 @@ int main(int argc, char** argv) {
   perf_case<256, 4, false>("encoder FFN2 shape", 32768, 768, 3072, sms, 10);
   perf_case<256, 4, false>("encoder QKV shape", 32768, 2304, 768, sms, 10);
   perf_case<128, 6, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case<192, 5, false, 8>("encoder FFN2 shape BN192", 32768, 768, 3072, sms, 10);
   perf_case<256, 4, true>("search 6980 x 1M", 6980, 1 << 20, 768, sms, 3);
   perf_case<256, 4, false>("search 6980 x 1M (n fastest)", 6980, 1 << 20, 768, sms, 3);
   perf_case<256, 4, false>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);

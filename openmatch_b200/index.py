@@ -102,6 +102,15 @@ class FlatIPIndex:
         _lib.check(self._lib.om_index_reserve(self._h, int(n), ctypes.byref(p)))
         return _wrap_device_f32(p.value, (int(n), self.d))
 
+    def master_rows(self) -> torch.Tensor:
+        """float32 CUDA view [ntotal, d] of the shard's master rows (no copy)."""
+        n = self.ntotal
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.om_index_reserve(self._h, 0, ctypes.byref(p)))  # address one past the last row
+        if n == 0:
+            return torch.empty((0, self.d), dtype=torch.float32, device="cuda")
+        return _wrap_device_f32(p.value - n * self.d * 4, (n, self.d))
+
     def commit_rows(self, n: int) -> None:
         _lib.check(self._lib.om_index_commit(self._h, int(n), _stream()))
 

@@ -110,7 +110,7 @@ class DRModel(nn.Module):
             self._cuda_encoders[key] = hit = (version, enc)
         return hit[1]
 
-    def encode(self, items, model, head):
+    def encode(self, items, model, head, need_hidden: bool = True):
         if items is None:
             return None, None
         decoder_path = "T5" in type(model).__name__ and not (self.model_args is not None and self.model_args.encoder_only)
@@ -130,11 +130,14 @@ class DRModel(nn.Module):
             for lo in range(0, B, max_b):
                 sl = slice(lo, lo + max_b)
                 tt = items.get("token_type_ids", None)
-                h, r = enc.encode(input_ids[sl], items["attention_mask"][sl], tt[sl] if tt is not None else None,
-                                  return_hidden=True)
-                hiddens.append(h)
+                r = enc.encode(input_ids[sl], items["attention_mask"][sl], tt[sl] if tt is not None else None,
+                               return_hidden=need_hidden)
+                if need_hidden:
+                    hiddens.append(r[0])
+                    r = r[1]
                 reps.append(r)
-            return (torch.cat(hiddens) if len(hiddens) > 1 else hiddens[0]), (torch.cat(reps) if len(reps) > 1 else reps[0])
+            hidden = (torch.cat(hiddens) if len(hiddens) > 1 else hiddens[0]) if need_hidden else None
+            return hidden, (torch.cat(reps) if len(reps) > 1 else reps[0])
         # training: HF module under autograd (bf16/fp16 autocast is applied by the trainer)
         out = model(**{k: v for k, v in items.items()}, return_dict=True)
         hidden = getattr(out, self.feature)
@@ -231,7 +234,9 @@ class DRModelForInference(DRModel):
     def encode_query(self, qry):
         return super().encode_query(qry)
 
+    @torch.no_grad()
     def forward(self, query: Dict[str, Tensor] = None, passage: Dict[str, Tensor] = None):
-        _, q_reps = self.encode_query(query)
-        _, p_reps = self.encode_passage(passage)
+        # the retriever only consumes the representations: skip the [B, L, H] last_hidden_state copy
+        _, q_reps = self.encode(query, self.lm_q, self.head_q, need_hidden=False)
+        _, p_reps = self.encode(passage, self.lm_p, self.head_p, need_hidden=False)
         return DROutput(q_reps=q_reps, p_reps=p_reps)

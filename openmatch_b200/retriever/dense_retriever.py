@@ -113,14 +113,9 @@ class Retriever:
             torch.distributed.barrier()
 
     def _index_rows_to_host(self) -> np.ndarray:
-        n = 0 if self.index is None else self.index.ntotal
-        if n == 0:
+        if self.index is None or self.index.ntotal == 0:
             return np.zeros((0, 0), dtype=np.float32)
-        # re-read the fp32 master rows of the shard: reserve(0) returns the address one past the last row
-        tail = self.index.reserve_rows(0)
-        base = tail.data_ptr() - n * self.index.d * 4
-        from ..index import _wrap_device_f32
-        return _wrap_device_f32(base, (n, self.index.d)).cpu().numpy()
+        return self.index.master_rows().cpu().numpy()  # one D2H copy per corpus shard
 
     def init_index_and_add(self, partition: str = None):
         logger.info("Initializing index from pre-computed document embeddings")

@@ -15,6 +15,9 @@ if len(sys.argv) > 1:
     cases = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 for N, nq, k in cases:
     idx = FlatIPIndex(d)
+    import os
+    if os.environ.get("OM_GROWTH"):
+        idx.set_param("round_growth", int(os.environ["OM_GROWTH"]))
     chunks = []
     done = 0
     while done < N:
