@@ -329,7 +329,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
   }
   {
     const int tok = row0 + tid;
-    s_kb[tid] = (tid < p.Tvalid_rows && tok < p.T) ? p.kmask[tok] : __int_as_float(0xff800000);
+    // key validity as 4 x 32-bit words (bit c%32 of word c/32): one ballot per warp
+    const bool key_ok = (tid < p.Tvalid_rows && tok < p.T) && p.kmask[tok] == 0.f;
+    const unsigned bits = __ballot_sync(0xffffffffu, key_ok);
+    if ((tid & 31) == 0) reinterpret_cast<uint32_t*>(s_kb)[warp] = bits;
     if (p.relbias_log2) {
       for (int i = tid; i < 2 * kMaxL - 1; i += 128) s_rel[i] = p.relbias_log2[head * (2 * kMaxL - 1) + i];
     }
@@ -363,20 +366,30 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
   const bool row_valid = r < p.Tvalid_rows && row0 + r < p.T;
   const int seq = r / p.L;
   const int c_lo = row_valid ? seq * p.L : 0, c_hi = row_valid ? c_lo + p.L : 0;
+  // this row may attend key c iff the key is valid AND belongs to the row's own sequence [c_lo, c_hi)
+  uint32_t allow[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int lo = c_lo - 32 * w, hi = c_hi - 32 * w;  // range relative to word w
+    const uint32_t ge = lo <= 0 ? 0xffffffffu : (lo >= 32 ? 0u : (0xffffffffu << lo));
+    const uint32_t lt = hi >= 32 ? 0xffffffffu : (hi <= 0 ? 0u : (0xffffffffu >> (32 - hi)));
+    allow[w] = reinterpret_cast<const uint32_t*>(s_kb)[w] & ge & lt;
+  }
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const bool has_rel = p.relbias_log2 != nullptr;
   float m = __int_as_float(0xff800000);
-#pragma unroll 1
+#pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
     uint32_t raw[32];
     tmem_ld_32x32b_x32(taddr + c4 * 32, raw);
     tmem_ld_wait();
+    const uint32_t aw = allow[c4];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int c = c4 * 32 + i;
-      float s = __uint_as_float(raw[i]) * p.scale_log2 + s_kb[c];
+      float s = __uint_as_float(raw[i]) * p.scale_log2;
       if (has_rel) s += s_rel[c - r + (kMaxL - 1)];
-      if (c < c_lo || c >= c_hi) s = __int_as_float(0xff800000);
+      if (!(aw & (1u << i))) s = __int_as_float(0xff800000);
       m = fmaxf(m, s);
     }
   }
@@ -384,11 +397,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
   const float mm = dead ? 0.f : m;
   float sum = 0.f;
   uint8_t* sP = smem + kAttnSmemP;
-#pragma unroll 1
+  const float neg_mm = -mm;
+#pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
     uint32_t raw[32];
     tmem_ld_32x32b_x32(taddr + c4 * 32, raw);
     tmem_ld_wait();
+    const uint32_t aw = dead ? 0u : allow[c4];
     uint32_t packed[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
@@ -396,10 +411,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int c = c4 * 32 + i + u;
-        float s = __uint_as_float(raw[i + u]) * p.scale_log2 + s_kb[c];
+        float s = fmaf(__uint_as_float(raw[i + u]), p.scale_log2, neg_mm);
         if (has_rel) s += s_rel[c - r + (kMaxL - 1)];
-        const bool off = (c < c_lo || c >= c_hi) || dead;
-        pv[u] = off ? 0.f : ex2_approx(s - mm);
+        pv[u] = (aw & (1u << (i + u))) ? ex2_approx(s) : 0.f;
       }
       sum += pv[0] + pv[1];
       packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);

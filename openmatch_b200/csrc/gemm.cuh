@@ -46,7 +46,8 @@ struct GemmCfg {
 //        column of the thread's next chunk (-1: none) so that global operands (residual) are always one
 //        chunk ahead of the math
 //   static constexpr int kSmemBytes = 0;                       > 0: that much dynamic smem is reserved for the functor
-//        and handed over through bind(State&, uint8_t* smem, int epilogue_thread_index) before begin()
+//        and handed over through bind(State&, uint8_t* smem, int epilogue_thread_index) once per thread; the
+//        State object persists across the thread's tiles and finish(State&) is called after the last one
 //   end() runs AFTER the thread's warp has released the accumulator buffer: long-latency tails (atomics,
 //        global stores) placed there overlap the next tile's MMAs
 //   static constexpr int kPasses = 1;                          2: the accumulator tile is read twice,
@@ -159,13 +160,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     static_assert((BN / 32) % (EPI_WARPS / 4) == 0, "column chunks must split evenly over the epilogue warps");
     constexpr int kChunks = BN / 32 / (EPI_WARPS / 4);
     int it = 0;
+    typename Epi::State st;  // lives across tiles: functors may keep work in flight from one tile to the next
+    if constexpr (Epi::kSmemBytes > 0) epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
       const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int row = m_blk * kBlockM + ew * 32 + lane;
-      typename Epi::State st;
-      if constexpr (Epi::kSmemBytes > 0) epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
       epi.begin(st, row, m_blk, n_blk);
       if constexpr (Epi::kPrefetch) epi.prefetch(st, row, n_blk * BN + half * kChunks * 32);  // before the wait
       mbar_wait_warp(&tfull_bar[as], aphase, 4);
@@ -218,6 +219,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       epi.end(st, row);
     }
+    if constexpr (Epi::kSmemBytes > 0) epi.finish(st);  // drain whatever the functor still has in flight
   }
 
   tc_fence_before_sync();

@@ -77,6 +77,9 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#if defined(OM_SPIN_SLEEP_NS) && OM_SPIN_SLEEP_NS > 0
+    __nanosleep(OM_SPIN_SLEEP_NS);
+#endif
     if ((++spins & 1023u) != 0) continue;
     if (*reinterpret_cast<volatile unsigned int*>(&om_dev_fault) != 0u) return;
     if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {
@@ -95,12 +98,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 // warp parks at __syncwarp.  Hundreds of threads spinning on try_wait compete with the TMA/MMA threads for
 // the barrier unit: measured 2x slowdown of the scan kernel when all 256 epilogue threads polled.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, uint32_t site) {
+#ifdef OM_EPI_ALL_LANES_WAIT
+  if (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(OM_EPI_ALL_LANES_WAIT);
+  }
+  return;
+#endif
   if ((threadIdx.x & 31u) == 0) {
     if (!mbar_try_wait(bar, parity)) {
       const long long t0 = clock64();
       uint32_t spins = 0;
       while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(64);
+#ifndef OM_EPI_POLL_SLEEP_NS
+#define OM_EPI_POLL_SLEEP_NS 64
+#endif
+        __nanosleep(OM_EPI_POLL_SLEEP_NS);
         if ((++spins & 1023u) != 0) continue;
         if (*reinterpret_cast<volatile unsigned int*>(&om_dev_fault) != 0u) break;
         if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {

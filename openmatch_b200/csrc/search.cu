@@ -28,125 +28,9 @@
 
 #include "common.h"
 #include "gemm.cuh"
+#include "scan_epilogue.cuh"
 
 namespace om {
-
-// ---------------------------------------------------------------------------------------------------
-// candidate keys: descending unsigned order == (score descending, row ascending)
-// ---------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t f32_orderable(float s) {
-  s = s + 0.0f;  // -0 -> +0
-#ifdef __CUDA_ARCH__
-  uint32_t u = __float_as_uint(s);
-#else
-  uint32_t u;
-  memcpy(&u, &s, 4);
-#endif
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__host__ __device__ __forceinline__ float f32_from_orderable(uint32_t u) {
-  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(u);
-#else
-  float s;
-  memcpy(&s, &u, 4);
-  return s;
-#endif
-}
-__host__ __device__ __forceinline__ unsigned long long make_key(float s, uint32_t row) {
-  return (static_cast<unsigned long long>(f32_orderable(s)) << 32) | static_cast<unsigned long long>(0xffffffffu - row);
-}
-__host__ __device__ __forceinline__ uint32_t key_row(unsigned long long k) {
-  return 0xffffffffu - static_cast<uint32_t>(k & 0xffffffffull);
-}
-__host__ __device__ __forceinline__ float key_score(unsigned long long k) {
-  return f32_from_orderable(static_cast<uint32_t>(k >> 32));
-}
-
-// ---------------------------------------------------------------------------------------------------
-// fused scan epilogue
-// ---------------------------------------------------------------------------------------------------
-template <bool DENSE>
-struct EpiScan {
-  const float* thr;          // [nq] strict lower bound per query
-  unsigned long long* cand;  // [nq, C]
-  int* count;                // [nq]
-  int* overflow;             // single flag
-  int nq, n_cols, C;
-  uint32_t row_base;  // corpus row of column 0 of this round
-  // DENSE: first round, every score is stored at position = column (no threshold yet)
-  // One pass over the accumulator tile.  A thread compares its 32-column chunks against its query's
-  // threshold and parks the rare survivors in a private shared-memory stash; the accumulator buffer is then
-  // released to the MMA warp, and only afterwards (end()) does the thread reserve slots in the query's
-  // candidate list with ONE atomicAdd and copy the stash out.  The L2 round trip of the atomic therefore
-  // overlaps the next tile's MMAs instead of holding a TMEM buffer (measured: the MMA warp was waiting for
-  // the epilogue on every tile when the append happened before the release).
-  static constexpr int kPasses = 1;
-  static constexpr bool kPrefetch = false;
-  static constexpr int kStash = 12;                     // survivors a thread can park per tile
-  static constexpr int kEpiThreads = 256;               // 8 epilogue warps
-  static constexpr int kSmemBytes = kStash * kEpiThreads * 8;
-  struct State {
-    float t;
-    int k, tid;
-    unsigned long long* stash;  // [kStash][kEpiThreads], this thread owns column `tid`
-  };
-  __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const {
-    s.stash = reinterpret_cast<unsigned long long*>(smem);
-    s.tid = epi_tid;
-  }
-  __device__ __forceinline__ void begin(State& s, int row, int, int) const {
-    s.t = (row < nq && !DENSE) ? thr[row] : __int_as_float(0x7f800000);
-    s.k = 0;
-  }
-  __device__ __noinline__ void flush(State& s, int row) const {
-    const int n = s.k;
-    const int pos = atomicAdd(count + row, n);
-    unsigned long long* mine = cand + static_cast<size_t>(row) * C;
-    for (int j = 0; j < n; ++j)
-      if (pos + j < C) mine[pos + j] = s.stash[j * kEpiThreads + s.tid];
-    if (pos + n > C) *overflow = 1;
-    s.k = 0;
-  }
-  __device__ __forceinline__ void end(State& s, int row) const {
-    if (s.k > 0) flush(s, row);
-  }
-  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
-    if (row >= nq || col0 >= n_cols) return;
-    if constexpr (DENSE) {
-      unsigned long long* mine = cand + static_cast<size_t>(row) * C;
-      if (col0 + 32 <= n_cols) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          ulonglong2 kk;
-          kk.x = make_key(v[i], row_base + col0 + i);
-          kk.y = make_key(v[i + 1], row_base + col0 + i + 1);
-          *reinterpret_cast<ulonglong2*>(mine + col0 + i) = kk;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < n_cols) mine[col0 + i] = make_key(v[i], row_base + col0 + i);
-      }
-      return;
-    }
-    const float t = s.t;
-    const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
-    float mx = v[0];
-#pragma unroll
-    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
-    if (!(mx > t)) return;  // common case: nothing in this chunk beats the threshold
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (v[i] > t && i < lim) {
-        if (s.k == kStash) flush(s, row);  // dense early rounds: spill while still holding the accumulator
-        s.stash[s.k * kEpiThreads + s.tid] = make_key(v[i], row_base + col0 + i);
-        ++s.k;
-      }
-    }
-  }
-};
 
 // ---------------------------------------------------------------------------------------------------
 // shared-memory bitonic sort (descending) of P = 2^m keys by nthreads threads

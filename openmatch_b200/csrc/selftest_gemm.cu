@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "scan_epilogue.cuh"
 
 using namespace om;
 
@@ -159,6 +160,56 @@ static void perf_case(const char* name, int M, int N, int K, int num_sms, int it
   cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
 }
 
+// the product's scan epilogue on the search shape, thresholds set so that nothing survives
+template <int EW>
+static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value) {
+  __nv_bfloat16 *dA, *dB;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  {
+    std::vector<uint16_t> h((size_t)1 << 22);
+    for (auto& x : h) x = (uint16_t)(0x3c00 + (rnd() % 0x400)) | (uint16_t)((rnd() & 1) << 15);
+    for (size_t off = 0; off < (size_t)M * K; off += h.size())
+      CK(cudaMemcpy(dA + off, h.data(), std::min(h.size(), (size_t)M * K - off) * 2, cudaMemcpyHostToDevice));
+    // different values for B (A == B rows would make |x|^2-sized scores), and a period that is not a multiple
+    // of the row length
+    std::vector<uint16_t> hb(((size_t)1 << 22) + 4099);
+    for (auto& x : hb) x = (uint16_t)(0x3c00 + ((rnd() >> 3) % 0x400)) | (uint16_t)(((rnd() >> 5) & 1) << 15);
+    for (size_t off = 0; off < (size_t)N * K; off += hb.size())
+      CK(cudaMemcpy(dB + off, hb.data(), std::min(hb.size(), (size_t)N * K - off) * 2, cudaMemcpyHostToDevice));
+  }
+  const int C = 4096;
+  float* thr;
+  unsigned long long* cand;
+  int *count, *ovf;
+  CK(cudaMalloc(&thr, M * 4));
+  CK(cudaMalloc(&cand, (size_t)M * C * 8));
+  CK(cudaMalloc(&count, M * 4));
+  CK(cudaMalloc(&ovf, 4));
+  std::vector<float> ht(M, thr_value);
+  CK(cudaMemcpy(thr, ht.data(), M * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(count, 0, M * 4));
+  CK(cudaMemset(ovf, 0, 4));
+  EpiScan<false, EW * 32> epi{thr, cand, count, ovf, M, N, C, 0u};
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= iters;
+  int hovf = 0;
+  CK(cudaMemcpy(&hovf, ovf, 4, cudaMemcpyDeviceToHost));
+  printf("[perf] %-28s EpiScan EW=%d thr=%g  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x ovf=%d\n", name, EW,
+         thr_value, M, N, K, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
+  cudaFree(dA), cudaFree(dB), cudaFree(thr), cudaFree(cand), cudaFree(count), cudaFree(ovf);
+}
+
 int main(int argc, char** argv) {
   const char* dump_dir = argc > 1 ? argv[1] : nullptr;
   cudaDeviceProp prop;
@@ -188,6 +239,12 @@ int main(int argc, char** argv) {
   perf_case<128, 6, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
   perf_case<192, 5, false, 8>("encoder FFN2 shape BN192", 32768, 768, 3072, sms, 10);
   perf_case<256, 4, true>("search 6980 x 1M", 6980, 1 << 20, 768, sms, 3);
+  perf_case<256, 4, true, 8>("search 6980 x 1M, 8 epi warps", 6980, 1 << 20, 768, sms, 3);
+  perf_scan<8>("scan epilogue, no survivors", 6980, 1 << 20, 768, sms, 3, 1e30f);
+  perf_scan<4>("scan epilogue, no survivors", 6980, 1 << 20, 768, sms, 3, 1e30f);
+  perf_scan<8>("scan epilogue, thr 3.1 sigma", 6980, 1 << 20, 768, sms, 3, 33.0f);
+  perf_scan<8>("scan epilogue, thr 2.3 sigma", 6980, 1 << 20, 768, sms, 3, 25.0f);
+  perf_scan<8>("scan epilogue, 4M rows", 6980, 1 << 22, 768, sms, 2, 1e30f);
   perf_case<256, 4, false>("search 6980 x 1M (n fastest)", 6980, 1 << 20, 768, sms, 3);
   perf_case<256, 4, false>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
   printf("SELFTEST OK\n");

@@ -1,6 +1,7 @@
 """Scratch probe (not part of the product): search timing + full-size validity property on the GPU.
 Property (size independent): for each checked query, no corpus row scores above the k-th returned score
 (counted with an independent torch fp32 GEMM), and returned scores equal torch's scores of those ids."""
+import os
 import sys
 import time
 
@@ -27,7 +28,7 @@ for N, nq, k in cases:
         chunks.append(c)
         done += n
     q = torch.randn(nq, d, device="cuda")
-    for it in range(3):
+    for it in range(int(os.environ.get('OM_ITERS', 3))):
         torch.cuda.synchronize()
         t1 = time.time()
         D, I = idx.search_device(q, k)
