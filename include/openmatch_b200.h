@@ -111,7 +111,7 @@ int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int
                     om_memkind out_kind, int64_t id_offset, void* stream);
 /* Tunables: "rescore_slack" (extra bf16-stage candidates kept per query; default max(64, k/8)),
  * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing),
- * "round_growth" (2..8, default 4: each scan round covers (g-1) x the rows already seen),
+ * "round_growth" (2..8, default 2: each scan round covers (g-1) x the rows already seen),
  * "profile" (1 = bracket every kernel launch of a search with CUDA events on the launching stream). */
 int om_index_set_param(om_index* idx, const char* name, int64_t value);
 /* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity),

@@ -50,9 +50,10 @@ struct GemmCfg {
 //        State object persists across the thread's tiles and finish(State&) is called after the last one
 //   end() runs AFTER the thread's warp has released the accumulator buffer: long-latency tails (atomics,
 //        global stores) placed there overlap the next tile's MMAs
-//   static constexpr int kPasses = 1;                          2: the accumulator tile is read twice,
-//        chunk(..., int pass) is called for pass 0 then pass 1 with between(State&, int row) in between
-//        (TMEM re-reads are cheap; used by the search filter to count survivors before appending them)
+//   static constexpr int kPasses = 1;                          2: the accumulator tile may be read twice:
+//        chunk(..., int pass) runs for pass 0; if need_pass(State&, 1) (warp-uniform) is true, between(State&,
+//        row) and a second sweep with pass 1 follow (TMEM re-reads are cheap; the search filter uses this as
+//        its overflow path when a thread finds more survivors than its stash holds)
 // Rows >= M and columns >= N contain zeros (TMA out-of-bounds fill) and must be masked by the functor.
 
 template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
@@ -175,7 +176,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int pass = 0; pass < Epi::kPasses; ++pass) {
         if constexpr (Epi::kPasses > 1) {
-          if (pass > 0) epi.between(st, row);
+          if (pass > 0) {
+            if (!epi.need_pass(st, pass)) break;  // warp-uniform decision
+            epi.between(st, row);
+          }
         }
         // Software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is processed.  The
         // loop stays ROLLED over chunk pairs (two register buffers): fully unrolling it made the scan kernel

@@ -52,22 +52,23 @@ struct EpiScan {
   int nq, n_cols, C;
   uint32_t row_base;  // corpus row of column 0 of this round
   // DENSE: first round, every score is stored at position = column (no threshold yet)
-  // One pass over the accumulator tile.  A thread compares its 32-column chunks against its query's
-  // threshold and parks the rare survivors in a private shared-memory stash; the accumulator buffer is then
-  // released to the MMA warp.  end() ISSUES one atomicAdd that reserves the survivors' slots in the query's
-  // candidate list, but its result is consumed only at the end of the thread's NEXT tile (double-buffered
-  // stash): the L2 round trip of the atomic (~1.5 us, once per survivor event, ~10^8 events per sweep) is
-  // hidden behind a whole tile of work instead of stalling the warp.  Measured before this change: the scan
-  // ran at 45 % tensor-pipe utilisation with the epilogue warps parked on ATOMG.
-  static constexpr int kPasses = 1;
+  // Pass 0: a thread compares its 32-column chunks against its query's threshold and parks the rare
+  // survivors (up to kStash per tile) in a private shared-memory stash.  The accumulator buffer is then
+  // released to the MMA warp, and end() ISSUES one atomicAdd that reserves the survivors' slots in the
+  // query's candidate list; the atomic's result is consumed only at the end of the thread's NEXT tile
+  // (double-buffered stash), so its L2 round trip is hidden behind a whole tile of work.
+  // Overflow path (dense early rounds): if some lane of the warp found more than kStash survivors, the warp
+  // sweeps the tile a second time (pass 1) and those lanes append the excess synchronously.
+  // Everything is force-inlined and State never has its address taken, so it lives in registers.
+  static constexpr int kPasses = 2;
   static constexpr bool kPrefetch = false;
   static constexpr int kStash = 8;                      // survivors a thread can park per tile
   static constexpr int kEpiThreads = EPI_THREADS;       // 8 epilogue warps in the product
-  static constexpr int kSmemBytes = 2 * kStash * kEpiThreads * 8;
+  static constexpr int kSmemBytes = DENSE ? 0 : 2 * kStash * kEpiThreads * 8;
   struct State {
     float t;
-    int k, tid, buf;
-    unsigned long long* stash;  // [2][kStash][kEpiThreads], this thread owns column `tid` of buffer `buf`
+    int k, n, skip, pos2, tid, buf;
+    unsigned long long* stash;     // [2][kStash][kEpiThreads], this thread owns column `tid` of buffer `buf`
     int p_n, p_pos, p_row, p_buf;  // reservation in flight: p_n keys of buffer p_buf go to row p_row at p_pos
   };
   __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const {
@@ -75,11 +76,16 @@ struct EpiScan {
     s.tid = epi_tid;
     s.buf = 0;
     s.p_n = 0;
-    s.k = 0;
   }
+  __device__ __forceinline__ void finish(State& s) const { drain(s); }
   __device__ __forceinline__ void begin(State& s, int row, int, int) const {
     s.t = (row < nq && !DENSE) ? thr[row] : __int_as_float(0x7f800000);
     s.k = 0;
+    s.n = 0;
+    if constexpr (DENSE) {  // no stash / reservation in the dense round
+      s.p_n = 0;
+      s.buf = 0;
+    }
   }
   __device__ __forceinline__ unsigned long long* slot(const State& s, int buf, int j) const {
     return s.stash + (static_cast<size_t>(buf) * kStash + j) * kEpiThreads + s.tid;
@@ -93,18 +99,20 @@ struct EpiScan {
       s.p_n = 0;
     }
   }
-  // synchronous spill (dense early rounds: more than kStash survivors in one tile)
-  __device__ __noinline__ void spill(State& s, int row) const {
-    drain(s);
-    const int n = s.k;
-    const int pos = atomicAdd(count + row, n);
-    unsigned long long* mine = cand + static_cast<size_t>(row) * C;
-    for (int j = 0; j < n; ++j)
-      if (pos + j < C) mine[pos + j] = *slot(s, s.buf, j);
-    if (pos + n > C) *overflow = 1;
-    s.k = 0;
+  __device__ __forceinline__ bool need_pass(const State& s, int) const {
+    if constexpr (DENSE) return false;
+    return __any_sync(0xffffffffu, s.n > kStash);
+  }
+  __device__ __forceinline__ void between(State& s, int row) const {
+    s.skip = kStash;
+    s.pos2 = C;
+    if (s.n > kStash) {
+      s.pos2 = atomicAdd(count + row, s.n - kStash);
+      if (s.pos2 + (s.n - kStash) > C) *overflow = 1;
+    }
   }
   __device__ __forceinline__ void end(State& s, int row) const {
+    if constexpr (DENSE) return;
     drain(s);  // last tile's survivors: their atomic was issued a whole tile ago
     if (s.k > 0) {
       s.p_pos = atomicAdd(count + row, s.k);  // result first used by the next drain()
@@ -112,14 +120,12 @@ struct EpiScan {
       s.p_row = row;
       s.p_buf = s.buf;
       s.buf ^= 1;
-      s.k = 0;
     }
   }
-  __device__ __forceinline__ void finish(State& s) const { drain(s); }
-  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int pass) const {
     if (row >= nq || col0 >= n_cols) return;
+    unsigned long long* mine = cand + static_cast<size_t>(row) * C;
     if constexpr (DENSE) {
-      unsigned long long* mine = cand + static_cast<size_t>(row) * C;
       if (col0 + 32 <= n_cols) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -137,16 +143,33 @@ struct EpiScan {
     }
     const float t = s.t;
     const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
+    if (pass == 1 && s.n <= kStash) return;
     float mx = v[0];
 #pragma unroll
     for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
     if (!(mx > t)) return;  // common case: nothing in this chunk beats the threshold
+    if (pass == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (v[i] > t && i < lim) {
-        if (s.k == kStash) spill(s, row);  // dense early rounds: spill while still holding the accumulator
-        *slot(s, s.buf, s.k) = make_key(v[i], row_base + col0 + i);
-        ++s.k;
+      for (int i = 0; i < 32; ++i) {
+        if (v[i] > t && i < lim) {
+          if (s.k < kStash) {
+            *slot(s, s.buf, s.k) = make_key(v[i], row_base + col0 + i);
+            ++s.k;
+          }
+          ++s.n;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (v[i] > t && i < lim) {
+          if (s.skip > 0) {
+            --s.skip;
+          } else {
+            if (s.pos2 < C) mine[s.pos2] = make_key(v[i], row_base + col0 + i);
+            ++s.pos2;
+          }
+        }
       }
     }
   }

@@ -242,8 +242,8 @@ int main(int argc, char** argv) {
   perf_case<256, 4, true, 8>("search 6980 x 1M, 8 epi warps", 6980, 1 << 20, 768, sms, 3);
   perf_scan<8>("scan epilogue, no survivors", 6980, 1 << 20, 768, sms, 3, 1e30f);
   perf_scan<4>("scan epilogue, no survivors", 6980, 1 << 20, 768, sms, 3, 1e30f);
-  perf_scan<8>("scan epilogue, thr 3.1 sigma", 6980, 1 << 20, 768, sms, 3, 33.0f);
-  perf_scan<8>("scan epilogue, thr 2.3 sigma", 6980, 1 << 20, 768, sms, 3, 25.0f);
+  perf_scan<8>("scan epilogue, thr 45", 6980, 1 << 20, 768, sms, 3, 45.0f);
+  perf_scan<8>("scan epilogue, thr 38", 6980, 1 << 20, 768, sms, 3, 38.0f);
   perf_scan<8>("scan epilogue, 4M rows", 6980, 1 << 22, 768, sms, 2, 1e30f);
   perf_case<256, 4, false>("search 6980 x 1M (n fastest)", 6980, 1 << 20, 768, sms, 3);
   perf_case<256, 4, false>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
