@@ -59,7 +59,7 @@ struct GemmCfg {
 template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, Epi epi) {
+                    int K, Epi epi, int* tile_counter) {
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,6 +69,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint8_t* epi_smem = smem + Cfg::kBarOffset + 256;  // Epi::kSmemBytes of scratch owned by the epilogue functor
+  // dynamic tile scheduler (tile_counter != nullptr): the producer claims tile indices from a global counter
+  // and publishes them to the MMA and epilogue roles through a 4-deep smem ring
+  constexpr int kSched = 4;
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);
+  uint64_t* sempty_bar = sfull_bar + kSched;
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(sempty_bar + kSched);
+  const bool dyn = tile_counter != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
@@ -85,6 +92,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < kSched; ++i) {
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&sempty_bar[i], 1 + EPI_WARPS);  // MMA thread + one lane per epilogue warp
     }
     fence_barrier_init();
   }
@@ -105,8 +116,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------ TMA producer ------------------------------
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t stage = 0, phase = 0, sslot = 0, sphase = 0;
+      int tile = blockIdx.x;
+      if (dyn) {
+        tile = atomicAdd(tile_counter, 1);
+        if (tile >= num_tiles) tile = -1;
+      }
+      while (true) {
+        if (dyn) {  // publish (also the -1 sentinel) to the consumer roles
+          mbar_wait(&sempty_bar[sslot], sphase ^ 1u, 5);
+          tile_ring[sslot] = tile;
+          mbar_arrive(&sfull_bar[sslot]);
+          if (++sslot == kSched) {
+            sslot = 0;
+            sphase ^= 1u;
+          }
+          if (tile < 0) break;
+        } else if (tile >= num_tiles) {
+          break;
+        }
+        // claim the next tile now; the atomic's round trip overlaps this tile's loads
+        int next = dyn ? atomicAdd(tile_counter, 1) : tile + static_cast<int>(gridDim.x);
         const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
         const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
@@ -120,15 +150,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             phase ^= 1u;
           }
         }
+        tile = (dyn && next >= num_tiles) ? -1 : next;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, sslot = 0, sphase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+        if (dyn) {
+          mbar_wait(&sfull_bar[sslot], sphase, 6);
+          const int t = tile_ring[sslot];
+          mbar_arrive(&sempty_bar[sslot]);
+          if (++sslot == kSched) {
+            sslot = 0;
+            sphase ^= 1u;
+          }
+          if (t < 0) break;
+        } else if (tile >= num_tiles) {
+          break;
+        }
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
         tc_fence_after_sync();
@@ -163,7 +206,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int it = 0;
     typename Epi::State st;  // lives across tiles: functors may keep work in flight from one tile to the next
     if constexpr (Epi::kSmemBytes > 0) epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    uint32_t sslot = 0, sphase = 0;
+    for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+      if (dyn) {
+        mbar_wait_warp(&sfull_bar[sslot], sphase, 7);
+        tile = tile_ring[sslot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty_bar[sslot]);
+        if (++sslot == kSched) {
+          sslot = 0;
+          sphase ^= 1u;
+        }
+        if (tile < 0) break;
+      } else if (tile >= num_tiles) {
+        break;
+      }
       const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
       const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -236,9 +293,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // Host launcher.  A: [M, K] bf16 row pitch lda elements; B: [N, K] bf16 row pitch ldb elements.
 // Returns cudaSuccess / a CUDA error; tensor-map failures map to cudaErrorInvalidValue.
+// Pool of tile counters for the dynamic scheduler: launch i uses counter i % 64 (zeroed on the launching stream
+// just before the kernel), so up to 64 dynamically scheduled GEMMs may be in flight.
+static inline int* next_tile_counter(cudaStream_t stream) {
+  static int* pool = nullptr;
+  static unsigned next = 0;
+  if (!pool && cudaMalloc(&pool, 64 * sizeof(int)) != cudaSuccess) return nullptr;
+  int* c = pool + (next++ & 63u);
+  if (cudaMemsetAsync(c, 0, sizeof(int), stream) != cudaSuccess) return nullptr;
+  return c;
+}
+
+// dynamic_sched: claim tiles from a global counter instead of the static blockIdx + i * gridDim order.  With
+// the static order CTAs drift apart over thousands of tiles and stop sharing operand tiles in L2 (measured on
+// the search scan: 143 GB of DRAM reads for a 6.4 GB shard); the dynamic order keeps all CTAs on neighbouring
+// tiles.
 template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
 static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                                      const Epi& epi, int num_sms, cudaStream_t stream) {
+                                      const Epi& epi, int num_sms, cudaStream_t stream, bool dynamic_sched = false) {
   using Cfg = GemmCfg<BN, STAGES>;
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   CUtensorMap tmA, tmB;
@@ -256,8 +328,13 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
   }
   const int num_tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  int* counter = nullptr;
+  if (dynamic_sched) {
+    counter = next_tile_counter(stream);
+    if (!counter) return cudaErrorMemoryAllocation;
+  }
   kern<<<grid, kGemmProducerThreads + 32 * EPI_WARPS, Cfg::kSmemBytes + Epi::kSmemBytes, stream>>>(tmA, tmB, M, N, K,
-                                                                                                     epi);
+                                                                                                     epi, counter);
   return cudaGetLastError();
 }
 

@@ -265,6 +265,7 @@ struct om_index {
   __nv_bfloat16* xb = nullptr;
   int64_t rescore_slack = -1;
   int force_safe = 0;
+  int dynamic_sched = 1;  // claim scan tiles from a global counter (keeps CTAs on neighbouring corpus tiles)
   int growth = 2;  // each round scans (growth - 1) x the rows seen so far (2 measured best on B200)
   int64_t st_rounds = 0, st_retries = 0, st_capacity = 0, st_launches = 0;
   // optional per-phase device timing (CUDA events on the launching stream), enabled by set_param("profile", 1)
@@ -414,8 +415,10 @@ int om_index_set_param(om_index* ix, const char* name, int64_t value) {
   } else if (!strcmp(name, "round_growth")) {
     if (value < 2 || value > 8) return fail(OM_EINVAL, "round_growth must be in [2, 8]");
     ix->growth = static_cast<int>(value);
+  } else if (!strcmp(name, "dynamic_sched")) {
+    ix->dynamic_sched = value != 0;
   } else if (!strcmp(name, "profile")) {
-    ix->profile = value != 0;
+    ix->profile = static_cast<int>(value);
   } else {
     return fail(OM_EINVAL, "om_index_set_param: unknown parameter '%s'", name);
   }
@@ -471,6 +474,7 @@ void collect_profile(om_index* ix) {
     if (cudaEventElapsedTime(&ms, ix->ev[i], ix->ev[i + 1]) != cudaSuccess) continue;
     const int kind = ix->ev_kind[i / 2];
     (kind == 0 ? ix->st_scan_us : kind == 1 ? ix->st_select_us : ix->st_final_us) += ms * 1e3;
+    if (ix->profile >= 2) fprintf(stderr, "[om profile] launch %zu %s %.3f ms\n", i / 2, kind == 0 ? "scan" : kind == 1 ? "select" : "finalize", ms);
   }
   ix->ev_used = 0;
 }
@@ -511,10 +515,12 @@ int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, int grow
       cudaError_t e;
       if (first) {
         EpiScan<true> epi{w.thr, w.cand, w.count, w.overflow, nq, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
-        e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st);
+        e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st,
+                                         ix->dynamic_sched != 0);
       } else {
         EpiScan<false> epi{w.thr, w.cand, w.count, w.overflow, nq, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
-        e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st);
+        e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st,
+                                         ix->dynamic_sched != 0);
       }
       if (e != cudaSuccess) return fail(OM_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
     }

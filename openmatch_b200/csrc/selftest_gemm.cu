@@ -50,8 +50,8 @@ struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics 
 };
 
 template <int BN, int STAGES, bool MF, int EW = 4>
-static int check_case(int M, int N, int K, int num_sms, const char* dump_dir) {
-  printf("[case] BN=%d STAGES=%d M_FASTEST=%d EW=%d  M=%d N=%d K=%d ... ", BN, STAGES, (int)MF, EW, M, N, K);
+static int check_case(int M, int N, int K, int num_sms, const char* dump_dir, bool dyn = false) {
+  printf("[case] BN=%d STAGES=%d M_FASTEST=%d EW=%d dyn=%d  M=%d N=%d K=%d ... ", BN, STAGES, (int)MF, EW, (int)dyn, M, N, K);
   fflush(stdout);
   std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
   std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
@@ -72,7 +72,7 @@ static int check_case(int M, int N, int K, int num_sms, const char* dump_dir) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
-  cudaError_t e = launch_gemm<BN, STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  cudaError_t e = launch_gemm<BN, STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn);
   if (e != cudaSuccess) {
     printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
     return 1;
@@ -162,7 +162,7 @@ static void perf_case(const char* name, int M, int N, int K, int num_sms, int it
 
 // the product's scan epilogue on the search shape, thresholds set so that nothing survives
 template <int EW>
-static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value) {
+static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value, bool dyn = false) {
   __nv_bfloat16 *dA, *dB;
   CK(cudaMalloc(&dA, (size_t)M * K * 2));
   CK(cudaMalloc(&dB, (size_t)N * K * 2));
@@ -194,10 +194,10 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 2; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -205,8 +205,8 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   ms /= iters;
   int hovf = 0;
   CK(cudaMemcpy(&hovf, ovf, 4, cudaMemcpyDeviceToHost));
-  printf("[perf] %-28s EpiScan EW=%d thr=%g  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x ovf=%d\n", name, EW,
-         thr_value, M, N, K, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
+  printf("[perf] %-28s EpiScan EW=%d dyn=%d thr=%g  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x ovf=%d\n", name, EW,
+         (int)dyn, thr_value, M, N, K, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
   cudaFree(dA), cudaFree(dB), cudaFree(thr), cudaFree(cand), cudaFree(count), cudaFree(ovf);
 }
 
@@ -229,6 +229,9 @@ int main(int argc, char** argv) {
   fails += check_case<64, 4, false, 8>(300, 200, 128, sms, dump_dir);
   fails += check_case<192, 5, false, 8>(1000, 768, 768, sms, dump_dir);  // 192-wide tiles, odd chunk tail
   fails += check_case<192, 5, false, 4>(300, 500, 192, sms, dump_dir);
+  fails += check_case<256, 4, true, 8>(3000, 9000, 256, sms, dump_dir, true);   // dynamic tile scheduler
+  fails += check_case<256, 4, false, 4>(300, 520, 192, sms, dump_dir, true);    // fewer tiles than CTAs
+  fails += check_case<192, 5, false, 8>(2048, 768, 768, sms, dump_dir, true);
   if (fails) {
     printf("SELFTEST FAILED (%d cases)\n", fails);
     return 1;
@@ -245,6 +248,8 @@ int main(int argc, char** argv) {
   perf_scan<8>("scan epilogue, thr 45", 6980, 1 << 20, 768, sms, 3, 45.0f);
   perf_scan<8>("scan epilogue, thr 38", 6980, 1 << 20, 768, sms, 3, 38.0f);
   perf_scan<8>("scan epilogue, 4M rows", 6980, 1 << 22, 768, sms, 2, 1e30f);
+  perf_scan<8>("scan epilogue, 4M rows", 6980, 1 << 22, 768, sms, 2, 1e30f, true);
+  perf_scan<8>("scan epilogue, thr 45", 6980, 1 << 22, 768, sms, 2, 45.0f, true);
   perf_case<256, 4, false>("search 6980 x 1M (n fastest)", 6980, 1 << 20, 768, sms, 3);
   perf_case<256, 4, false>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
   printf("SELFTEST OK\n");

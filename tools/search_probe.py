@@ -17,6 +17,8 @@ if len(sys.argv) > 1:
 for N, nq, k in cases:
     idx = FlatIPIndex(d)
     import os
+    if os.environ.get("OM_PROFILE"):
+        idx.set_param("profile", int(os.environ["OM_PROFILE"]))
     if os.environ.get("OM_GROWTH"):
         idx.set_param("round_growth", int(os.environ["OM_GROWTH"]))
     chunks = []
