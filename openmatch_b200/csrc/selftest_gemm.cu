@@ -178,7 +178,7 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
     for (size_t off = 0; off < (size_t)N * K; off += hb.size())
       CK(cudaMemcpy(dB + off, hb.data(), std::min(hb.size(), (size_t)N * K - off) * 2, cudaMemcpyHostToDevice));
   }
-  const int C = 4096;
+  const int C = 1 << 16;
   float* thr;
   unsigned long long* cand;
   int *count, *ovf;
@@ -205,8 +205,16 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   ms /= iters;
   int hovf = 0;
   CK(cudaMemcpy(&hovf, ovf, 4, cudaMemcpyDeviceToHost));
-  printf("[perf] %-28s EpiScan EW=%d dyn=%d thr=%g  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x ovf=%d\n", name, EW,
-         (int)dyn, thr_value, M, N, K, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
+  // survivors per launch (count[] accumulated over warm-up + timed launches)
+  std::vector<int> hc(M);
+  CK(cudaMemcpy(hc.data(), count, M * 4, cudaMemcpyDeviceToHost));
+  double surv = 0;
+  for (int c : hc) surv += c;
+  surv /= (iters + 2);
+  printf("[perf] %-24s EpiScan EW=%d dyn=%d thr=%g N=%d : %.3f ms %.1f TFLOP/s fault=0x%x ovf=%d survivors/query=%.0f (%.2f per warp-tile)\n",
+         name, EW, (int)dyn, thr_value, N, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf,
+         surv / M, surv / M * 32.0 / (N / 256.0) / (EW / 4));
+  if (false) printf("%d %d %d %f", 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
   cudaFree(dA), cudaFree(dB), cudaFree(thr), cudaFree(cand), cudaFree(count), cudaFree(ovf);
 }
 
@@ -245,8 +253,8 @@ int main(int argc, char** argv) {
   perf_case<256, 4, true, 8>("search 6980 x 1M, 8 epi warps", 6980, 1 << 20, 768, sms, 3);
   perf_scan<8>("scan epilogue, no survivors", 6980, 1 << 20, 768, sms, 3, 1e30f);
   perf_scan<4>("scan epilogue, no survivors", 6980, 1 << 20, 768, sms, 3, 1e30f);
-  perf_scan<8>("scan epilogue, thr 45", 6980, 1 << 20, 768, sms, 3, 45.0f);
-  perf_scan<8>("scan epilogue, thr 38", 6980, 1 << 20, 768, sms, 3, 38.0f);
+  for (float t : {48.f, 42.f, 38.f, 35.f, 32.f}) perf_scan<8>("scan 1M", 6980, 1 << 20, 768, sms, 3, t, true);
+  perf_scan<8>("scan 1M static", 6980, 1 << 20, 768, sms, 3, 38.f, false);
   perf_scan<8>("scan epilogue, 4M rows", 6980, 1 << 22, 768, sms, 2, 1e30f);
   perf_scan<8>("scan epilogue, 4M rows", 6980, 1 << 22, 768, sms, 2, 1e30f, true);
   perf_scan<8>("scan epilogue, thr 45", 6980, 1 << 22, 768, sms, 2, 45.0f, true);
