@@ -32,52 +32,95 @@ constexpr float kLog2e = 1.4426950408889634f;
 // ===================================================================================================
 // GEMM epilogues
 // ===================================================================================================
-// GELU(x) = x/2 (1 + erf(x/sqrt 2)) with erf as the rational minimax x P(x^2)/Q(x^2) on [-4, 4]
-// (|err| < 5e-7, checked against math.erf): 12 FMA + 1 MUFU.RCP per element instead of erff()'s ~35
-// instructions, which made the FFN1 epilogue slower than the tensor cores.
-__device__ __forceinline__ float gelu_erf(float x) {
-  float z = fminf(fmaxf(x * 0.70710678118654752440f, -4.f), 4.f);
-  const float z2 = z * z;
-  float p = -2.72614225801306e-10f;
-  p = fmaf(p, z2, 2.77068142495902e-08f);
-  p = fmaf(p, z2, -2.10102402082508e-06f);
-  p = fmaf(p, z2, -5.69250639462346e-05f);
-  p = fmaf(p, z2, -7.34990630326855e-04f);
-  p = fmaf(p, z2, -2.95459980854025e-03f);
-  p = fmaf(p, z2, -1.60960333262415e-02f);
-  float q = -1.45660718464996e-05f;
-  q = fmaf(q, z2, -2.13374055278905e-04f);
-  q = fmaf(q, z2, -1.68282697438203e-03f);
-  q = fmaf(q, z2, -7.37332916720468e-03f);
-  q = fmaf(q, z2, -1.42647390514189e-02f);
-  const float erf = __fdividef(p * z, q);
-  const float hx = 0.5f * x;
-  return fmaf(hx, erf, hx);
+// GELU(x) = x/2 (1 + erf(x / sqrt 2)) for two elements per instruction (FFMA2): the FFN1 epilogue is ISSUE-bound
+// (with erff() / a 13-term rational it needed more issue cycles per tile than the tensor cores need for the
+// tile's MMAs), so erf is the cheapest approximation that is invisible after bf16 rounding of the output:
+// z P(z^2) / Q(z^2) on [-4, 4], P cubic, Q cubic with Q >= 1, fitted against math.erf: max |err| 2.1e-5
+// (bf16 output rounding is 2e-3 relative); 6 FFMA2 + 1 MUFU.RCP per element pair half.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-
-// two elements per instruction (FFMA2): the FFN1 epilogue is issue-bound, not latency-bound
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   float2 z = mul2(x, splat2(0.70710678118654752440f));
   z.x = fminf(fmaxf(z.x, -4.f), 4.f);
   z.y = fminf(fmaxf(z.y, -4.f), 4.f);
   const float2 z2 = mul2(z, z);
-  float2 p = fma2(splat2(-2.72614225801306e-10f), z2, splat2(2.77068142495902e-08f));
-  p = fma2(p, z2, splat2(-2.10102402082508e-06f));
-  p = fma2(p, z2, splat2(-5.69250639462346e-05f));
-  p = fma2(p, z2, splat2(-7.34990630326855e-04f));
-  p = fma2(p, z2, splat2(-2.95459980854025e-03f));
-  p = fma2(p, z2, splat2(-1.60960333262415e-02f));
-  float2 q = fma2(splat2(-1.45660718464996e-05f), z2, splat2(-2.13374055278905e-04f));
-  q = fma2(q, z2, splat2(-1.68282697438203e-03f));
-  q = fma2(q, z2, splat2(-7.37332916720468e-03f));
-  q = fma2(q, z2, splat2(-1.42647390514189e-02f));
-  const float2 num = mul2(p, z);
-  const float2 erf = make_float2(__fdividef(num.x, q.x), __fdividef(num.y, q.y));
+  float2 p = fma2(splat2(0.0006061712047085166f), z2, splat2(0.041214898228645325f));
+  p = fma2(p, z2, splat2(0.1745881289243698f));
+  p = fma2(p, z2, splat2(1.1282498836517334f));
+  float2 q = fma2(splat2(0.008151348680257797f), z2, splat2(0.10013707727193832f));
+  q = fma2(q, z2, splat2(0.48736122250556946f));
+  q = fma2(q, z2, splat2(1.0f));
+  const float2 erf = mul2(mul2(p, z), make_float2(rcp_approx(q.x), rcp_approx(q.y)));
   const float2 hx = mul2(x, splat2(0.5f));
   return fma2(hx, erf, hx);
 }
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+// Coalescing stage for bf16 epilogue outputs.  A thread owns one accumulator ROW, so a direct 16-byte store
+// per lane touches 32 different cache lines per warp instruction and the SM's load/store unit — not the tensor
+// core — bounds the GEMM (measured: tensor pipe ~50 % with direct stores, 92 % with no stores).  Instead two
+// consecutive 32-column chunks (= 128 bytes per row) are staged in a warp-private 4 KB shared-memory tile
+// (16-byte pieces XOR-swizzled by row) and written back row-wise: every warp store then covers 4 full 128-byte
+// lines.
+struct StagedBf16 {
+  static constexpr int kBytesPerWarp = 4096;
+  uint32_t held[16];  // first chunk of the pair, packed bf16x2
+  int have, held_col;
+  uint8_t* tile;
+  __device__ __forceinline__ void bind(uint8_t* smem, int epi_tid) {
+    tile = smem + (epi_tid >> 5) * kBytesPerWarp;
+    have = 0;
+  }
+  // direct (uncoalesced) store of one 32-column chunk: tail of an odd chunk count
+  __device__ __forceinline__ static void store_direct(const uint32_t (&pk)[16], __nv_bfloat16* out, int64_t ldo, int row,
+                                                      int col0, int M) {
+    if (row >= M) return;
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  }
+  // pk = packed chunk [col0, col0+32) of this lane's row; every lane of the warp must call this
+  __device__ __forceinline__ void push(const uint32_t (&pk)[16], __nv_bfloat16* out, int64_t ldo, int row, int col0, int M) {
+    if (!have) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) held[i] = pk[i];
+      have = 1;
+      held_col = col0;
+      return;
+    }
+    have = 0;
+    const int lane = threadIdx.x & 31;
+    uint8_t* mine = tile + lane * 128;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      *reinterpret_cast<uint4*>(mine + ((p ^ (lane & 7)) << 4)) =
+          make_uint4(held[4 * p], held[4 * p + 1], held[4 * p + 2], held[4 * p + 3]);
+      *reinterpret_cast<uint4*>(mine + (((p + 4) ^ (lane & 7)) << 4)) =
+          make_uint4(pk[4 * p], pk[4 * p + 1], pk[4 * p + 2], pk[4 * p + 3]);
+    }
+    __syncwarp();
+    const int row_base = row - lane;  // first row of this warp's 32-row slab
+    const int piece = lane & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rr = 4 * j + (lane >> 3);
+      const uint4 val = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((piece ^ (rr & 7)) << 4));
+      if (row_base + rr < M)
+        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row_base + rr) * ldo + held_col + piece * 8) = val;
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void flush_tail(__nv_bfloat16* out, int64_t ldo, int row, int M) {
+    if (have) {
+      store_direct(held, out, ldo, row, held_col, M);
+      have = 0;
+    }
+  }
+};
 
 // out bf16 [M, ldo] = act(acc + bias)
 template <int ACT>
@@ -88,12 +131,16 @@ struct EpiBiasActBf16 {
   int M, N;
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
-  static constexpr int kSmemBytes = 0;
-  struct State {};
-  __device__ __forceinline__ void begin(State&, int, int, int) const {}
-  __device__ __forceinline__ void end(State&, int) const {}
-  __device__ __forceinline__ void chunk(State&, int row, int col0, const float (&v)[32]) const {
-    if (row >= M || col0 >= N) return;  // N is a multiple of 32 for every encoder GEMM (checked on the host)
+  __host__ __device__ static constexpr int smem_bytes(int epi_warps) { return epi_warps * StagedBf16::kBytesPerWarp; }
+  struct State {
+    StagedBf16 stage;
+  };
+  __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const { s.stage.bind(smem, epi_tid); }
+  __device__ __forceinline__ void finish(State&) const {}
+  __device__ __forceinline__ void begin(State& s, int, int, int) const { s.stage.have = 0; }
+  __device__ __forceinline__ void end(State& s, int row) const { s.stage.flush_tail(out, ldo, row, M); }
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
+    if (col0 >= N) return;  // warp-uniform; N is a multiple of 32 for every encoder GEMM (checked on the host)
     uint32_t packed[16];
     float bv[32];
 #pragma unroll
@@ -112,9 +159,7 @@ struct EpiBiasActBf16 {
       }
       packed[i >> 1] = pack_bf16x2(ab.x, ab.y);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    s.stage.push(packed, out, ldo, row, col0, M);
   }
 };
 
@@ -131,16 +176,20 @@ struct EpiQKV {
   int valid_rows;     // tokens per attention tile (spt * L)
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
-  static constexpr int kSmemBytes = 0;
+  __host__ __device__ static constexpr int smem_bytes(int epi_warps) { return epi_warps * StagedBf16::kBytesPerWarp; }
   struct State {
     int vcol;
+    StagedBf16 stage;
   };
+  __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const { s.stage.bind(smem, epi_tid); }
+  __device__ __forceinline__ void finish(State&) const {}
   __device__ __forceinline__ void begin(State& s, int row, int, int) const {
     s.vcol = (row / valid_rows) * 128 + row % valid_rows;
+    s.stage.have = 0;
   }
-  __device__ __forceinline__ void end(State&, int) const {}
+  __device__ __forceinline__ void end(State& s, int row) const { s.stage.flush_tail(qk, I2, row, M); }
   __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
-    if (row >= M || col0 >= I2 + (I2 >> 1)) return;
+    if (col0 >= I2 + (I2 >> 1)) return;  // warp-uniform
     float bv[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -151,11 +200,8 @@ struct EpiQKV {
       uint32_t packed[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) packed[i >> 1] = pack_bf16x2(v[i] + bv[i], v[i + 1] + bv[i + 1]);
-      uint4* dst = reinterpret_cast<uint4*>(qk + static_cast<int64_t>(row) * I2 + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-    } else {
+      s.stage.push(packed, qk, I2, row, col0, M);
+    } else if (row < M) {
       __nv_bfloat16* dst = vt + static_cast<int64_t>(col0 - I2) * ldv + s.vcol;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
@@ -217,18 +263,35 @@ __device__ __forceinline__ void affine_store(const float4 (&v)[kMaxVec], int nve
     }
 }
 
-// y = Norm(h) * gamma (+ beta); writes fp32 (nullable, may alias h) and bf16 (nullable)
-template <bool RMS>
-__global__ void __launch_bounds__(128) norm_kernel(const float* h, const float* gamma, const float* beta, float eps,
-                                                   int T, int H, float* out_f32, __nv_bfloat16* out_bf16) {
+// sum = h (+ add); y = Norm(sum) * gamma (+ beta).  Writes sum back to h when STORE_SUM (T5's pre-norm residual
+// stream), y as fp32 (nullable, may alias h: BERT's post-LN stream / T5's final norm) and as bf16 (nullable: the
+// next GEMM's A operand).  `add` is the bf16 output of the preceding O-proj / FFN2 GEMM: doing the residual add
+// here keeps those GEMM epilogues store-only — with the fp32 residual read in the epilogue they were bound by
+// exposed DRAM latency (tensor pipe 20 % on O-proj) — and this kernel streams at HBM speed anyway.
+template <bool RMS, bool STORE_SUM>
+__global__ void __launch_bounds__(128) norm_kernel(float* h, const __nv_bfloat16* __restrict__ add, const float* gamma,
+                                                   const float* beta, float eps, int T, int H, float* out_f32,
+                                                   __nv_bfloat16* out_bf16) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   const int nvec = H >> 7;
   float4 v[kMaxVec];
-  const float* src = h + static_cast<int64_t>(row) * H;
+  float* src = h + static_cast<int64_t>(row) * H;
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j)
     if (j < nvec) v[j] = *reinterpret_cast<const float4*>(src + (j * 32 + lane) * 4);
+  if (add) {
+    const __nv_bfloat16* a = add + static_cast<int64_t>(row) * H;
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+      if (j < nvec) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(a + (j * 32 + lane) * 4);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        v[j].x += lo.x, v[j].y += lo.y, v[j].z += hi.x, v[j].w += hi.y;
+        if (STORE_SUM) *reinterpret_cast<float4*>(src + (j * 32 + lane) * 4) = v[j];
+      }
+  }
   norm_row<RMS>(v, nvec, H, eps);
   affine_store(v, nvec, lane, gamma, beta, out_f32 ? out_f32 + static_cast<int64_t>(row) * H : nullptr,
                out_bf16 ? out_bf16 + static_cast<int64_t>(row) * H : nullptr);
@@ -586,7 +649,7 @@ struct om_encoder {
   // workspace
   int Tmax = 0, Tld = 0;
   float *h = nullptr, *kmask = nullptr, *pooled = nullptr, *headed = nullptr;
-  __nv_bfloat16 *xb = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *inter = nullptr;
+  __nv_bfloat16 *xb = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *inter = nullptr, *obuf = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -738,6 +801,7 @@ int om_encoder_create(const om_encoder_desc* desc, om_encoder** out) {
   A(&e->vt, (size_t)I * e->Tld);
   A(&e->ctx, T * I);
   A(&e->inter, T * F);
+  A(&e->obuf, T * H);
   A(&e->pooled, T * H);  // at most Tmax sequences (L >= 1)
   A(&e->headed, (size_t)e->Tmax * std::max(d.head_out, 1));
   if (rc != 0) {
@@ -960,9 +1024,14 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       make_tmap_bf16_2d(&tmVt, e->vt, (uint64_t)n_tiles * 128, (uint64_t)I, (uint64_t)e->Tld * 2, 64, 64) != 0)
     return fail(OM_ECUDA, "om_encode: tensor map creation failed");
 
+  // `pending` = bf16 output of the last O-proj / FFN2 GEMM that has not been added to the residual stream yet
+  const __nv_bfloat16* pending = nullptr;
   for (int li = 0; li < d.layers; ++li) {
     const LayerW& w = e->layers[li];
-    if (!bert) norm_kernel<true><<<rows4, 128, 0, st>>>(e->h, w.ln1_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
+    if (!bert) {  // T5 pre-norm: h += pending; x = RMSNorm(h)
+      norm_kernel<true, true><<<rows4, 128, 0, st>>>(e->h, pending, w.ln1_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
+      pending = nullptr;
+    }
     {
       EpiQKV epi{e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, spt * L};
       cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
@@ -971,17 +1040,17 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
     OM_CUDA(cudaGetLastError());
     {
-      EpiStoreF32 epi{e->h, H, bert ? w.bo : nullptr, e->h, H, T, H};
       // N = H: 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
-      // waves of full tiles): less wave-quantisation loss on 148 SMs
-      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 5, false, 8>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st)
+      // waves of full tiles): less wave-quantisation loss on 148 SMs.  Store-only epilogue (bf16).
+      EpiBiasActBf16<ACT_NONE> epi{e->obuf, H, bert ? w.bo : nullptr, T, H};
+      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st)
                                        : launch_gemm<256, 4, false, 8>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "O-proj GEMM launch failed: %s", cudaGetErrorString(err));
     }
-    if (bert)
-      norm_kernel<false><<<rows4, 128, 0, st>>>(e->h, w.ln1_g, w.ln1_b, d.ln_eps, T, H, e->h, e->xb);
-    else
-      norm_kernel<true><<<rows4, 128, 0, st>>>(e->h, w.ln2_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
+    if (bert)  // h = LN(h + o)
+      norm_kernel<false, false><<<rows4, 128, 0, st>>>(e->h, e->obuf, w.ln1_g, w.ln1_b, d.ln_eps, T, H, e->h, e->xb);
+    else  // h += o; x = RMSNorm(h)
+      norm_kernel<true, true><<<rows4, 128, 0, st>>>(e->h, e->obuf, w.ln2_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
     {
       cudaError_t err;
       if (bert) {
@@ -994,15 +1063,19 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN1 GEMM launch failed: %s", cudaGetErrorString(err));
     }
     {
-      EpiStoreF32 epi{e->h, H, bert ? w.b2 : nullptr, e->h, H, T, H};
-      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 5, false, 8>(e->inter, F, w.w2, F, T, H, F, epi, sms, st)
+      EpiBiasActBf16<ACT_NONE> epi{e->obuf, H, bert ? w.b2 : nullptr, T, H};
+      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->inter, F, w.w2, F, T, H, F, epi, sms, st)
                                        : launch_gemm<256, 4, false, 8>(e->inter, F, w.w2, F, T, H, F, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN2 GEMM launch failed: %s", cudaGetErrorString(err));
     }
-    if (bert) norm_kernel<false><<<rows4, 128, 0, st>>>(e->h, w.ln2_g, w.ln2_b, d.ln_eps, T, H, e->h, e->xb);
+    if (bert)
+      norm_kernel<false, false><<<rows4, 128, 0, st>>>(e->h, e->obuf, w.ln2_g, w.ln2_b, d.ln_eps, T, H, e->h, e->xb);
+    else
+      pending = e->obuf;  // added by the next layer's first norm (or the final norm)
     OM_CUDA(cudaGetLastError());
   }
-  if (!bert) norm_kernel<true><<<rows4, 128, 0, st>>>(e->h, e->final_g, nullptr, d.ln_eps, T, H, e->h, nullptr);
+  if (!bert)  // final_layer_norm over h + pending
+    norm_kernel<true, false><<<rows4, 128, 0, st>>>(e->h, pending, e->final_g, nullptr, d.ln_eps, T, H, e->h, nullptr);
   if (out_hidden)
     OM_CUDA(cudaMemcpyAsync(out_hidden, e->h, static_cast<size_t>(T) * H * 4, cudaMemcpyDeviceToDevice, st));
 

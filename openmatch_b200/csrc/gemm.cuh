@@ -8,9 +8,10 @@
 //                                             double-buffered (2 x BN columns)
 //   warp 2                     TMEM allocator
 //   warps 4..4+EPI_WARPS       epilogue     : tcgen05.ld -> registers -> Epi functor (fused op).
-//                                             EPI_WARPS = 4: one thread per accumulator row; 8: two threads
-//                                             per row, each owning half of the tile's columns (for
-//                                             math-heavy epilogues such as bias + erf-GELU)
+//                                             EPI_WARPS = 4: one thread per accumulator row; 8 / 16: two / four
+//                                             threads per row, each owning a column group of the tile (math-
+//                                             heavy epilogues such as bias + erf-GELU need the extra warps to
+//                                             hide TMEM-load and MUFU latency)
 //
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue); static persistent
 // tile schedule (tile = blockIdx.x + i * gridDim.x).
@@ -45,7 +46,7 @@ struct GemmCfg {
 //        thread's first chunk BEFORE waiting on the accumulator, and chunk(..., int next_col0) receives the
 //        column of the thread's next chunk (-1: none) so that global operands (residual) are always one
 //        chunk ahead of the math
-//   static constexpr int kSmemBytes = 0;                       > 0: that much dynamic smem is reserved for the functor
+//   __host__ __device__ static constexpr int smem_bytes(int epi_warps);            > 0: that much dynamic smem is reserved for the functor
 //        and handed over through bind(State&, uint8_t* smem, int epilogue_thread_index) once per thread; the
 //        State object persists across the thread's tiles and finish(State&) is called after the last one
 //   end() runs AFTER the thread's warp has released the accumulator buffer: long-latency tails (atomics,
@@ -198,14 +199,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS must be 4 or 8");
+    static_assert(EPI_WARPS == 4 || EPI_WARPS == 8 || EPI_WARPS == 12 || EPI_WARPS == 16, "EPI_WARPS: 4, 8, 12 or 16");
     const int ew = (warp - 4) & 3;      // == warp % 4: the TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;   // column half owned by this warp when EPI_WARPS == 8
+    const int half = (warp - 4) >> 2;   // column group (of EPI_WARPS / 4) owned by this warp
     static_assert((BN / 32) % (EPI_WARPS / 4) == 0, "column chunks must split evenly over the epilogue warps");
     constexpr int kChunks = BN / 32 / (EPI_WARPS / 4);
     int it = 0;
     typename Epi::State st;  // lives across tiles: functors may keep work in flight from one tile to the next
-    if constexpr (Epi::kSmemBytes > 0) epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
+    if constexpr (Epi::smem_bytes(EPI_WARPS) > 0)
+      epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
     uint32_t sslot = 0, sphase = 0;
     for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
       if (dyn) {
@@ -280,7 +282,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       epi.end(st, row);
     }
-    if constexpr (Epi::kSmemBytes > 0) epi.finish(st);  // drain whatever the functor still has in flight
+    if constexpr (Epi::smem_bytes(EPI_WARPS) > 0) epi.finish(st);  // drain whatever the functor still has in flight
   }
 
   tc_fence_before_sync();
@@ -322,7 +324,7 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes + Epi::kSmemBytes);
+                                         Cfg::kSmemBytes + Epi::smem_bytes(EPI_WARPS));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -333,7 +335,7 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
     counter = next_tile_counter(stream);
     if (!counter) return cudaErrorMemoryAllocation;
   }
-  kern<<<grid, kGemmProducerThreads + 32 * EPI_WARPS, Cfg::kSmemBytes + Epi::kSmemBytes, stream>>>(tmA, tmB, M, N, K,
+  kern<<<grid, kGemmProducerThreads + 32 * EPI_WARPS, Cfg::kSmemBytes + Epi::smem_bytes(EPI_WARPS), stream>>>(tmA, tmB, M, N, K,
                                                                                                      epi, counter);
   return cudaGetLastError();
 }
@@ -350,7 +352,7 @@ struct EpiStoreF32 {  // C fp32 = acc (+ bias[n]) (+ resid[m, n])
   int M, N;
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = true;
-  static constexpr int kSmemBytes = 0;
+  __host__ __device__ static constexpr int smem_bytes(int) { return 0; }
   struct State {
     float4 pre[8];  // residual of the chunk about to be processed
   };

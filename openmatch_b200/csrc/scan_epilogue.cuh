@@ -64,7 +64,7 @@ struct EpiScan {
   static constexpr bool kPrefetch = false;
   static constexpr int kStash = 8;                      // survivors a thread can park per tile
   static constexpr int kEpiThreads = EPI_THREADS;       // 8 epilogue warps in the product
-  static constexpr int kSmemBytes = DENSE ? 0 : 2 * kStash * kEpiThreads * 8;
+  __host__ __device__ static constexpr int smem_bytes(int) { return DENSE ? 0 : 2 * kStash * kEpiThreads * 8; }
   struct State {
     float t;
     int k, n, skip, pos2, tid, buf;

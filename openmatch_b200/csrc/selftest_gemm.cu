@@ -35,7 +35,7 @@ struct EpiCount {  // perf probe: counts accumulators above a threshold (mimics 
   int M, N;
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
-  static constexpr int kSmemBytes = 0;
+  __host__ __device__ static constexpr int smem_bytes(int) { return 0; }
   struct State {
     int cnt;
   };
