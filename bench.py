@@ -137,6 +137,7 @@ def main():
         print(json.dumps(line))
         return
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
 
@@ -273,11 +274,15 @@ def main():
     scan_flops = 2.0 * nq * n_local * d * args.steps
     scan_s = scan_ns * 1e-9
     achieved = scan_flops / scan_s / 1e12 if scan_s > 0 else None
-    traffic = None
+    traffic = traffic_note = None
     tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_note = "%s: %.3g B DRAM vs %.3g B algorithmic (x%.3f); %s" % (
+            tj.get("launch"), traffic, tj.get("algorithmic_bytes_per_launch"), tj.get("ratio_traffic_over_algorithmic"),
+            tj.get("source"))
     line = {
         "metric": "queries/sec top-1000 over 8.8M x 768 corpus", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -292,6 +297,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops"] if achieved else None, "traffic": traffic,
+                     "traffic_note": traffic_note,
                      "kernel": "gemm_bf16_tn_kernel<256,4,1,8,EpiScan> (fused Q*X^T + top-k filter)",
                      "note": "2*nq*rows*d FLOPs per sweep / CUDA-event time of the scan launches on the launching "
                              "stream; " + peaks["source"],
