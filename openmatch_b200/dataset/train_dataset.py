@@ -29,8 +29,15 @@ class DRTrainDataset(IterableDataset):
     def create_one_example(self, token_ids: List[int], is_query: bool = False):
         max_len = self.data_args.q_max_len if is_query else self.data_args.p_max_len
         if self.tokenizer is not None:
-            return self.tokenizer.encode_plus(token_ids, truncation="only_first", max_length=max_len, padding=False,
-                                              return_attention_mask=False, return_token_type_ids=False)
+            # the reference calls tokenizer.encode_plus(ids, truncation='only_first', max_length=...) (:62-70);
+            # that API no longer exists in transformers 5.x, so special tokens are added explicitly
+            if not hasattr(self, "_affix"):
+                empty = list(self.tokenizer("", add_special_tokens=True)["input_ids"])  # e.g. [CLS, SEP] / [</s>]
+                k = 1 if len(empty) >= 2 else 0
+                self._affix = (empty[:k], empty[k:])
+            prefix, suffix = self._affix
+            room = max(max_len - len(prefix) - len(suffix), 0)
+            return {"input_ids": prefix + list(token_ids)[:room] + suffix}
         return {"input_ids": list(token_ids)[:max_len]}
 
     def _pick(self, example, epoch: int, hashed_seed):
@@ -59,9 +66,10 @@ class DRTrainDataset(IterableDataset):
         hashed_seed = hash(self.trainer.args.seed) if self.trainer is not None else self.shuffle_seed
         records = (json.loads(line) for path in self.data_files for line in open(path) if line.strip())
         if self.shuffle_seed is not None:  # buffered shuffle, like datasets' streaming shuffle
-            rng, buf = random.Random(self.shuffle_seed + epoch), []
+            rng, buf, source = random.Random(self.shuffle_seed + epoch), [], records
+
             def shuffled():
-                for rec in records:
+                for rec in source:
                     buf.append(rec)
                     if len(buf) >= 10_000:
                         yield buf.pop(rng.randrange(len(buf)))
