@@ -14,7 +14,6 @@
 // Activations feeding tensor cores are bf16; the residual stream, normalisation statistics, softmax,
 // pooling, head and L2-normalisation are fp32.
 #include <math.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -1025,10 +1024,6 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       make_tmap_bf16_2d(&tmVt, e->vt, (uint64_t)n_tiles * 128, (uint64_t)I, (uint64_t)e->Tld * 2, 64, 64) != 0)
     return fail(OM_ECUDA, "om_encode: tensor map creation failed");
 
-  static const bool dyn = [] {  // experiment switch: claim encoder GEMM tiles from a global counter
-    const char* v = getenv("OM_ENC_DYN");
-    return v && v[0] == '1';
-  }();
   // `pending` = bf16 output of the last O-proj / FFN2 GEMM that has not been added to the residual stream yet
   const __nv_bfloat16* pending = nullptr;
   for (int li = 0; li < d.layers; ++li) {
@@ -1039,7 +1034,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     }
     {
       EpiQKV epi{e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, spt * L};
-      cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st, dyn);
+      cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
     }
     attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
@@ -1048,7 +1043,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       // N = H: 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
       // waves of full tiles): less wave-quantisation loss on 148 SMs.  Store-only epilogue (bf16).
       EpiBiasActBf16<ACT_NONE> epi{e->obuf, H, bert ? w.bo : nullptr, T, H};
-      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st, dyn)
+      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st)
                                        : launch_gemm<256, 4, false, 8>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "O-proj GEMM launch failed: %s", cudaGetErrorString(err));
     }
@@ -1060,16 +1055,16 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       cudaError_t err;
       if (bert) {
         EpiBiasActBf16<ACT_GELU> epi{e->inter, F, w.b1, T, F};
-        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st, dyn);
+        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
       } else {
         EpiBiasActBf16<ACT_RELU> epi{e->inter, F, nullptr, T, F};
-        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st, dyn);
+        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
       }
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN1 GEMM launch failed: %s", cudaGetErrorString(err));
     }
     {
       EpiBiasActBf16<ACT_NONE> epi{e->obuf, H, bert ? w.b2 : nullptr, T, H};
-      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->inter, F, w.w2, F, T, H, F, epi, sms, st, dyn)
+      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->inter, F, w.w2, F, T, H, F, epi, sms, st)
                                        : launch_gemm<256, 4, false, 8>(e->inter, F, w.w2, F, T, H, F, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN2 GEMM launch failed: %s", cudaGetErrorString(err));
     }
