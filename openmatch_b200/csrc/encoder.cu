@@ -63,17 +63,18 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 // Coalescing stage for bf16 epilogue outputs.  A thread owns one accumulator ROW, so a direct 16-byte store
 // per lane touches 32 different cache lines per warp instruction and the SM's load/store unit — not the tensor
 // core — bounds the GEMM (measured: tensor pipe ~50 % with direct stores, 92 % with no stores).  Instead two
-// consecutive 32-column chunks (= 128 bytes per row) are staged in a warp-private 4 KB shared-memory tile
-// (16-byte pieces XOR-swizzled by row) and written back row-wise: every warp store then covers 4 full 128-byte
-// lines.
+// consecutive 32-column chunks (= 128 bytes per row) are written into a warp-private 4 KB shared-memory tile
+// in the TMA SWIZZLE_128B layout (16-byte pieces XOR-ed with row & 7) and ONE lane issues a TMA store of the
+// 32-row x 64-column box: no LSU work for the global write, rows beyond M are clipped by the tensor map.
 struct StagedBf16 {
   static constexpr int kBytesPerWarp = 4096;
   uint32_t held[16];  // first chunk of the pair, packed bf16x2
-  int have, held_col;
+  int have, held_col, in_flight;
   uint8_t* tile;
   __device__ __forceinline__ void bind(uint8_t* smem, int epi_tid) {
-    tile = smem + (epi_tid >> 5) * kBytesPerWarp;
+    tile = smem + (epi_tid >> 5) * kBytesPerWarp;  // 1024-byte aligned (swizzle atom)
     have = 0;
+    in_flight = 0;
   }
   // direct (uncoalesced) store of one 32-column chunk: tail of an odd chunk count
   __device__ __forceinline__ static void store_direct(const uint32_t (&pk)[16], __nv_bfloat16* out, int64_t ldo, int row,
@@ -84,7 +85,7 @@ struct StagedBf16 {
     for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
   }
   // pk = packed chunk [col0, col0+32) of this lane's row; every lane of the warp must call this
-  __device__ __forceinline__ void push(const uint32_t (&pk)[16], __nv_bfloat16* out, int64_t ldo, int row, int col0, int M) {
+  __device__ __forceinline__ void push(const uint32_t (&pk)[16], const CUtensorMap* tm_out, int row, int col0) {
     if (!have) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) held[i] = pk[i];
@@ -94,6 +95,10 @@ struct StagedBf16 {
     }
     have = 0;
     const int lane = threadIdx.x & 31;
+    if (in_flight) {  // the previous TMA store must have finished reading the tile
+      if (lane == 0) bulk_wait_group_read0();
+      __syncwarp();
+    }
     uint8_t* mine = tile + lane * 128;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -102,17 +107,13 @@ struct StagedBf16 {
       *reinterpret_cast<uint4*>(mine + (((p + 4) ^ (lane & 7)) << 4)) =
           make_uint4(pk[4 * p], pk[4 * p + 1], pk[4 * p + 2], pk[4 * p + 3]);
     }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA (async proxy)
     __syncwarp();
-    const int row_base = row - lane;  // first row of this warp's 32-row slab
-    const int piece = lane & 7;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int rr = 4 * j + (lane >> 3);
-      const uint4 val = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((piece ^ (rr & 7)) << 4));
-      if (row_base + rr < M)
-        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row_base + rr) * ldo + held_col + piece * 8) = val;
+    if (lane == 0) {
+      tma_store_2d(tm_out, tile, held_col, row);  // lane 0's row is the first row of the warp's 32-row slab
+      bulk_commit_group();
     }
-    __syncwarp();
+    in_flight = 1;
   }
   __device__ __forceinline__ void flush_tail(__nv_bfloat16* out, int64_t ldo, int row, int M) {
     if (have) {
@@ -120,11 +121,15 @@ struct StagedBf16 {
       have = 0;
     }
   }
+  __device__ __forceinline__ void finish() {
+    if (in_flight && (threadIdx.x & 31) == 0) bulk_wait_group0();
+  }
 };
 
 // out bf16 [M, ldo] = act(acc + bias)
 template <int ACT>
 struct EpiBiasActBf16 {
+  CUtensorMap tm_out;  // box {64 cols, 32 rows} over out, SWIZZLE_128B (TMA store)
   __nv_bfloat16* out;
   int64_t ldo;
   const float* bias;  // nullable
@@ -136,7 +141,7 @@ struct EpiBiasActBf16 {
     StagedBf16 stage;
   };
   __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const { s.stage.bind(smem, epi_tid); }
-  __device__ __forceinline__ void finish(State&) const {}
+  __device__ __forceinline__ void finish(State& s) const { s.stage.finish(); }
   __device__ __forceinline__ void begin(State& s, int, int, int) const { s.stage.have = 0; }
   __device__ __forceinline__ void end(State& s, int row) const { s.stage.flush_tail(out, ldo, row, M); }
   __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
@@ -159,7 +164,7 @@ struct EpiBiasActBf16 {
       }
       packed[i >> 1] = pack_bf16x2(ab.x, ab.y);
     }
-    s.stage.push(packed, out, ldo, row, col0, M);
+    s.stage.push(packed, &tm_out, row, col0);
   }
 };
 
@@ -168,6 +173,7 @@ struct EpiBiasActBf16 {
 // token m of attention tile m / valid_rows sits at column tile * 128 + m % valid_rows, so every tile's
 // V^T box starts at a 256-byte aligned column.
 struct EpiQKV {
+  CUtensorMap tm_qk;  // box {64 cols, 32 rows} over qk, SWIZZLE_128B (TMA store)
   __nv_bfloat16* qk;
   __nv_bfloat16* vt;
   int64_t ldv;
@@ -182,7 +188,7 @@ struct EpiQKV {
     StagedBf16 stage;
   };
   __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const { s.stage.bind(smem, epi_tid); }
-  __device__ __forceinline__ void finish(State&) const {}
+  __device__ __forceinline__ void finish(State& s) const { s.stage.finish(); }
   __device__ __forceinline__ void begin(State& s, int row, int, int) const {
     s.vcol = (row / valid_rows) * 128 + row % valid_rows;
     s.stage.have = 0;
@@ -200,7 +206,7 @@ struct EpiQKV {
       uint32_t packed[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) packed[i >> 1] = pack_bf16x2(v[i] + bv[i], v[i + 1] + bv[i + 1]);
-      s.stage.push(packed, qk, I2, row, col0, M);
+      s.stage.push(packed, &tm_qk, row, col0);
     } else if (row < M) {
       __nv_bfloat16* dst = vt + static_cast<int64_t>(col0 - I2) * ldv + s.vcol;
 #pragma unroll
@@ -1024,6 +1030,12 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       make_tmap_bf16_2d(&tmVt, e->vt, (uint64_t)n_tiles * 128, (uint64_t)I, (uint64_t)e->Tld * 2, 64, 64) != 0)
     return fail(OM_ECUDA, "om_encode: tensor map creation failed");
 
+  // TMA-store tensor maps of the three bf16 GEMM outputs (box = 64 columns x 32 rows = one epilogue warp's pair)
+  CUtensorMap tmQKout, tmObuf, tmInter;
+  if (make_tmap_bf16_2d(&tmQKout, e->qk, (uint64_t)2 * I, (uint64_t)T, (uint64_t)2 * I * 2, 64, 32) != 0 ||
+      make_tmap_bf16_2d(&tmObuf, e->obuf, (uint64_t)H, (uint64_t)T, (uint64_t)H * 2, 64, 32) != 0 ||
+      make_tmap_bf16_2d(&tmInter, e->inter, (uint64_t)F, (uint64_t)T, (uint64_t)F * 2, 64, 32) != 0)
+    return fail(OM_ECUDA, "om_encode: output tensor map creation failed");
   // `pending` = bf16 output of the last O-proj / FFN2 GEMM that has not been added to the residual stream yet
   const __nv_bfloat16* pending = nullptr;
   for (int li = 0; li < d.layers; ++li) {
@@ -1033,7 +1045,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       pending = nullptr;
     }
     {
-      EpiQKV epi{e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, spt * L};
+      EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, spt * L};
       cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
     }
@@ -1042,7 +1054,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     {
       // N = H: 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
       // waves of full tiles): less wave-quantisation loss on 148 SMs.  Store-only epilogue (bf16).
-      EpiBiasActBf16<ACT_NONE> epi{e->obuf, H, bert ? w.bo : nullptr, T, H};
+      EpiBiasActBf16<ACT_NONE> epi{tmObuf, e->obuf, H, bert ? w.bo : nullptr, T, H};
       cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st)
                                        : launch_gemm<256, 4, false, 8>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "O-proj GEMM launch failed: %s", cudaGetErrorString(err));
@@ -1054,16 +1066,16 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     {
       cudaError_t err;
       if (bert) {
-        EpiBiasActBf16<ACT_GELU> epi{e->inter, F, w.b1, T, F};
+        EpiBiasActBf16<ACT_GELU> epi{tmInter, e->inter, F, w.b1, T, F};
         err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
       } else {
-        EpiBiasActBf16<ACT_RELU> epi{e->inter, F, nullptr, T, F};
+        EpiBiasActBf16<ACT_RELU> epi{tmInter, e->inter, F, nullptr, T, F};
         err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
       }
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN1 GEMM launch failed: %s", cudaGetErrorString(err));
     }
     {
-      EpiBiasActBf16<ACT_NONE> epi{e->obuf, H, bert ? w.b2 : nullptr, T, H};
+      EpiBiasActBf16<ACT_NONE> epi{tmObuf, e->obuf, H, bert ? w.b2 : nullptr, T, H};
       cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->inter, F, w.w2, F, T, H, F, epi, sms, st)
                                        : launch_gemm<256, 4, false, 8>(e->inter, F, w.w2, F, T, H, F, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN2 GEMM launch failed: %s", cudaGetErrorString(err));

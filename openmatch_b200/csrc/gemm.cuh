@@ -33,7 +33,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kSmemBytes = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
+  static constexpr int kEpiOffset = kBarOffset + 1024;         // epilogue scratch starts 1024-B aligned (TMA store)
+  static constexpr int kSmemBytes = kEpiOffset + 1024;         // + slack for 1024-B alignment of the base
   static constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // power of two >= 2 * BN
 };
 
@@ -60,7 +61,7 @@ struct GemmCfg {
 template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, Epi epi, int* tile_counter) {
+                    int K, const __grid_constant__ Epi epi, int* tile_counter) {
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,7 +70,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* epi_smem = smem + Cfg::kBarOffset + 256;  // Epi::kSmemBytes of scratch owned by the epilogue functor
+  uint8_t* epi_smem = smem + Cfg::kEpiOffset;  // Epi::smem_bytes() of scratch owned by the epilogue functor
   // dynamic tile scheduler (tile_counter != nullptr): the producer claims tile indices from a global counter
   // and publishes them to the MMA and epilogue roles through a 4-deep smem ring
   constexpr int kSched = 4;
