@@ -202,6 +202,8 @@ class Retriever:
         are gathered to rank 0, which alone builds the result dict (like the reference, :200-203)."""
         dist = torch.distributed
         W, r = self.args.world_size, self.args.process_index
+        if self.index is None:  # this rank holds no rows (fewer embedding files than ranks)
+            self._initialize_faiss_index(encoded.shape[1])
         offset, _ = shard_offsets(len(self.doc_lookup))
         q = torch.from_numpy(np.ascontiguousarray(encoded, dtype=np.float32)).to(self.args.device)
         Dl, Il = self.index.search_device(q, topk, id_offset=offset)

@@ -32,6 +32,7 @@ def _check(got, want, what, rel_tol=1e-2, cos_tol=0.9999):
     assert np.isfinite(got).all(), what + ": non-finite output"
     assert rel <= rel_tol, "%s: rel-L2 %.3e > %.1e" % (what, rel, rel_tol)
     assert cos.min() >= cos_tol, "%s: min cosine %.6f < %.4f" % (what, cos.min(), cos_tol)
+    print("[parity] %-28s rel-L2 %.2e (tol %.0e)  min cosine %.6f" % (what, rel, rel_tol, cos.min()))
     return rel, cos.min()
 
 
