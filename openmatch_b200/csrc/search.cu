@@ -53,16 +53,18 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* s, int P, 
   }
 }
 
-// SELECT: one CTA per query.  MSB-first radix select (8-bit digits) of the kp-th largest key among the cnt
-// candidates, then compaction of the keys >= it to the head of the list (unordered) and publication of its
-// score as the new strict threshold.  (A full shared-memory sort here costs ~35 GB of smem traffic per
-// round at nq = 6980 — it was 43 % of the search time; selection needs 8 read-only passes.)
+// SELECT: one CTA per query.  MSB-first radix select of the kp-th largest key among the cnt candidates, then
+// compaction of the keys >= it to the head of the list (unordered) and publication of its score as the new
+// strict threshold.  The 32 score bits are resolved with three 11/11/10-bit passes; the 32 row bits are only
+// walked (four 8-bit passes) when the kp-th score is tied with more candidates than there are slots left.
+// (A full shared-memory sort here costs ~35 GB of smem traffic per round at nq = 6980 — it was 43 % of the
+// search time.)
 __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, int* count, float* thr, int C, int kp,
                                                      int cnt_override) {
   extern __shared__ unsigned long long skeys[];
-  __shared__ int hist[256];
+  __shared__ int hist[2048];
   __shared__ unsigned long long s_prefix;
-  __shared__ int s_remaining, s_out;
+  __shared__ int s_remaining, s_out, s_bin_count;
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   unsigned long long* mine = cand + static_cast<size_t>(q) * C;
   int cnt = cnt_override >= 0 ? cnt_override : count[q];
@@ -82,28 +84,29 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
   }
   __syncthreads();
   unsigned long long mask = 0ull;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    hist[tid] = 0;
+  // digit schedule: (shift, bits)
+  const int shifts[7] = {53, 42, 32, 24, 16, 8, 0};
+  const int widths[7] = {11, 11, 10, 8, 8, 8, 8};
+  for (int pass = 0; pass < 7; ++pass) {
+    const int shift = shifts[pass], nbins = 1 << widths[pass];
+    for (int i = tid; i < nbins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const unsigned long long prefix = s_prefix;
     for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
       const int i = i0 + tid;
       const bool live = i < cnt && (skeys[i] & mask) == prefix;
-      const int digit = live ? static_cast<int>((skeys[i] >> shift) & 255ull) : -1;
-      // warp-aggregate equal digits (top bytes of similar scores collide heavily)
+      const int digit = live ? static_cast<int>((skeys[i] >> shift) & static_cast<unsigned long long>(nbins - 1)) : -1;
+      // warp-aggregate equal digits (top bits of similar scores collide heavily)
       const unsigned peers = __match_any_sync(0xffffffffu, digit);
       if (live && lane == (__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
     }
     __syncthreads();
     if (tid < 32) {
-      // lane l owns digits 255-8l .. 248-8l (descending); find the digit where the running count from the
-      // top reaches `remaining`
-      int local[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        local[j] = hist[255 - (lane * 8 + j)];
-        sum += local[j];
-      }
+      // lane l owns the bins [nbins - (l+1)*per, nbins - l*per) scanned from the top; find the bin where the
+      // running count from the top reaches `remaining`
+      const int per = nbins >> 5;
+      int sum = 0;
+      for (int j = 0; j < per; ++j) sum += hist[nbins - 1 - (lane * per + j)];
       int incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -114,23 +117,28 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
       __syncwarp();
       if (excl < remaining && remaining <= incl) {  // exactly one lane
         int run = excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (run < remaining && remaining <= run + local[j]) {
-            s_prefix = prefix | (static_cast<unsigned long long>(255 - (lane * 8 + j)) << shift);
+        for (int j = 0; j < per; ++j) {
+          const int bin = nbins - 1 - (lane * per + j), c = hist[bin];
+          if (run < remaining && remaining <= run + c) {
+            s_prefix = prefix | (static_cast<unsigned long long>(bin) << shift);
             s_remaining = remaining - run;
+            s_bin_count = c;
           }
-          run += local[j];
+          run += c;
         }
       }
     }
-    mask |= 255ull << shift;
+    mask |= static_cast<unsigned long long>(nbins - 1) << shift;
     __syncthreads();
+    // after the score bits: if every candidate sharing the kp-th score fits, no need to look at row bits
+    if (pass == 2 && s_bin_count == s_remaining) break;
   }
-  const unsigned long long kth = s_prefix;  // keys are unique, so exactly kp keys are >= kth
+  // keys >= kth under `mask` (keys are unique, so with all 64 bits resolved exactly kp keys qualify; with only
+  // the score bits resolved the whole tie group qualifies and it fits by the check above)
+  const unsigned long long kth = s_prefix;
   for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
     const int i = i0 + tid;
-    if (i < cnt && skeys[i] >= kth) mine[atomicAdd(&s_out, 1)] = skeys[i];
+    if (i < cnt && (skeys[i] & mask) >= kth) mine[atomicAdd(&s_out, 1)] = skeys[i];
   }
   if (tid == 0) {
     count[q] = kp;

@@ -66,6 +66,7 @@ class DRModel(nn.Module):
         self.feature, self.pooling, self.normalize = feature, pooling, normalize
         self.model_args, self.train_args, self.data_args = model_args, train_args, data_args
         self._cuda_encoders = {}  # (id(lm), id(head)) -> (weights version, CudaEncoder)
+        self.force_torch_path = False  # GradCache's no-grad representation pass must match its autograd pass
         if train_args is not None and train_args.negatives_x_device:
             if not dist.is_initialized():
                 raise ValueError('Distributed training has not been initialized for representation all gather.')
@@ -96,7 +97,7 @@ class DRModel(nn.Module):
 
     # ------------------------------------------------------------------ encode
     def _needs_autograd(self) -> bool:
-        return torch.is_grad_enabled() and self.training
+        return self.force_torch_path or (torch.is_grad_enabled() and self.training)
 
     def _cuda_encoder(self, model, head):
         from ..encoder import CudaEncoder

@@ -1,3 +1,3 @@
-from .dense_trainer import DRTrainer, GCDenseTrainer
+from .dense_trainer import DRTrainer, GCDenseTrainer, get_dense_rep, split_dense_inputs
 
-__all__ = ["DRTrainer", "GCDenseTrainer"]
+__all__ = ["DRTrainer", "GCDenseTrainer", "split_dense_inputs", "get_dense_rep"]

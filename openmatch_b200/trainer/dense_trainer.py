@@ -205,10 +205,84 @@ class DRTrainer:
             self._save(output_dir)
 
 
+def split_dense_inputs(model_input: dict, chunk_size: int):
+    """{'query' | 'passage': {name: tensor [B, ...]}} -> list of the same structure over row chunks
+    (reference dense_trainer.py:111-120)."""
+    assert len(model_input) == 1
+    key, tensors = next(iter(model_input.items()))
+    names = list(tensors.keys())
+    pieces = [tensors[n].split(chunk_size, dim=0) for n in names]
+    return [{key: dict(zip(names, chunk))} for chunk in zip(*pieces)]
+
+
+def get_dense_rep(x):
+    return x.p_reps if x.q_reps is None else x.q_reps
+
+
 class GCDenseTrainer(DRTrainer):
-    """Gradient-cache training depends on the un-vendored ``grad_cache`` package (reference
-    dense_trainer.py:20-24,130-160); it is outside the current hot-path scope."""
+    """Gradient-cache training (reference dense_trainer.py:130-160, which delegates to the un-vendored
+    ``grad_cache`` package).  Restated here from GradCache's published algorithm:
+      1. encode every query / passage chunk WITHOUT autograd (remembering the RNG state of each chunk);
+      2. evaluate the contrastive loss on the concatenated representations — the fused CUDA loss kernel returns
+         d loss / d reps directly, which is exactly the "gradient cache";
+      3. re-encode each chunk WITH autograd under its saved RNG state and back-propagate the surrogate
+         <reps_chunk, cached_grad_chunk>.
+    Peak activation memory is one chunk; the in-batch negatives span the whole (optionally cross-device) batch."""
 
     def __init__(self, *args, **kwargs):
-        raise NotImplementedError("GradCache training needs the external `grad_cache` package and is not part of the "
-                                  "B200 hot path yet; train with DRTrainer (--grad_cache False)")
+        super().__init__(*args, **kwargs)
+        from ..loss import DistributedContrastiveLoss, SimpleContrastiveLoss
+        self.loss_fn = DistributedContrastiveLoss() if self.args.negatives_x_device else SimpleContrastiveLoss()
+        self.chunk_sizes = [self.args.gc_q_chunk_size, self.args.gc_p_chunk_size]
+
+    def _encode_chunks(self, model, chunks, with_grad, rng_states=None):
+        reps, states = [], []
+        for i, chunk in enumerate(chunks):
+            if rng_states is not None:
+                torch.cuda.set_rng_state(rng_states[i])
+            states.append(torch.cuda.get_rng_state())
+            with self._autocast(), (nullcontext() if with_grad else torch.no_grad()):
+                reps.append(get_dense_rep(model(**chunk)))
+        return reps, states
+
+    def training_step(self, model, inputs) -> torch.Tensor:
+        model.train()
+        queries, passages = self._prepare_inputs(inputs)
+        q_chunks = split_dense_inputs({"query": queries}, self.chunk_sizes[0])
+        p_chunks = split_dense_inputs({"passage": passages}, self.chunk_sizes[1])
+        # 1. representation pass, no graph (same torch encoder + dropout streams as pass 3, not the CUDA
+        #    inference encoder)
+        core = model.module if hasattr(model, "module") else model
+        core.force_torch_path = True
+        try:
+            q_reps, q_rng = self._encode_chunks(model, q_chunks, with_grad=False)
+            p_reps, p_rng = self._encode_chunks(model, p_chunks, with_grad=False)
+        finally:
+            core.force_torch_path = False
+        # 2. loss + gradient cache w.r.t. the representations
+        q_all = torch.cat(q_reps).float().requires_grad_()
+        p_all = torch.cat(p_reps).float().requires_grad_()
+        loss = self.loss_fn(q_all, p_all)
+        if self.args.gradient_accumulation_steps > 1:
+            loss = loss / self.args.gradient_accumulation_steps
+        loss.backward()
+        q_cache = q_all.grad.split(self.chunk_sizes[0])
+        p_cache = p_all.grad.split(self.chunk_sizes[1])
+        # 3. chunked forward-backward against the cached gradients (DDP all-reduces only on the last chunk)
+        todo = [(c, g, q_rng[i]) for i, (c, g) in enumerate(zip(q_chunks, q_cache))] + \
+               [(c, g, p_rng[i]) for i, (c, g) in enumerate(zip(p_chunks, p_cache))]
+        saved = torch.cuda.get_rng_state()
+        for j, (chunk, grad, state) in enumerate(todo):
+            last = j == len(todo) - 1
+            sync_ctx = nullcontext() if (last or not hasattr(model, "no_sync")) else model.no_sync()
+            with sync_ctx:
+                torch.cuda.set_rng_state(state)
+                with self._autocast():
+                    reps = get_dense_rep(model(**chunk))
+                surrogate = (reps.float() * grad).sum()
+                if self._scaler is not None:
+                    self._scaler.scale(surrogate).backward()
+                else:
+                    surrogate.backward()
+        torch.cuda.set_rng_state(saved)
+        return loss.detach() / self._dist_loss_scale_factor

@@ -119,3 +119,34 @@ def test_training_reduces_loss(workdir):
     losses = [e["loss"] for e in trainer.state.log_history]
     assert len(losses) == 12 and np.isfinite(losses).all()
     assert np.mean(losses[-3:]) < np.mean(losses[:3]), losses
+
+
+def test_grad_cache_matches_plain_step(workdir):
+    """GCDenseTrainer (chunked, gradient cache) must produce the same parameter gradients as one plain step."""
+    from openmatch.arguments import DataArguments, DRTrainingArguments, ModelArguments
+    from openmatch.dataset import DRTrainDataset, QPCollator
+    from openmatch.modeling import DRModel
+    from openmatch.trainer import DRTrainer, GCDenseTrainer
+    margs = ModelArguments(model_name_or_path=str(workdir / "model"))
+    dargs = DataArguments(train_path=str(workdir / "train.jsonl"), train_n_passages=4, q_max_len=8, p_max_len=16)
+
+    def grads(trainer_cls, **extra):
+        targs = DRTrainingArguments(output_dir=str(workdir / "ckpt3"), per_device_train_batch_size=8, max_steps=1,
+                                    dataloader_num_workers=0, **extra)
+        torch.manual_seed(0)
+        model = DRModel.build(margs, dargs, targs).cuda()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        trainer = trainer_cls(model=model, args=targs, train_dataset=DRTrainDataset(None, dargs),
+                              data_collator=QPCollator(None, 8, 16))
+        trainer._scaler = None
+        batch = next(iter(trainer.get_train_dataloader()))
+        loss = trainer.training_step(model, batch)
+        g = model.lm_q.encoder.layer[1].output.dense.weight.grad.detach().float().cpu().numpy().copy()
+        return float(loss), g
+
+    l0, g0 = grads(DRTrainer)
+    l1, g1 = grads(GCDenseTrainer, grad_cache=True, gc_q_chunk_size=3, gc_p_chunk_size=8)
+    assert abs(l0 - l1) <= 1e-3 * max(1.0, abs(l0))
+    assert np.linalg.norm(g0 - g1) <= 2e-2 * np.linalg.norm(g0)
