@@ -143,7 +143,7 @@ def main():
 
     from openmatch_b200 import synthetic
     from openmatch_b200.encoder import CudaEncoder
-    from openmatch_b200.index import FlatIPIndex, exchange_and_merge
+    from openmatch_b200.index import FlatIPIndex, sharded_search_device
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -183,8 +183,9 @@ def main():
     torch.cuda.synchronize()
 
     def search_step(q):
-        Dl, Il = idx.search_device(q, k, id_offset=lo)
-        return exchange_and_merge(Dl, Il, k)  # world > 1: NCCL all-gather of [nq, k] lists + merge kernel
+        # world > 1: local scan -> all-reduce(MAX) of per-query floors -> pruned fp32 re-score -> NCCL all-gather of
+        # the [nq, k] lists -> merge kernel
+        return sharded_search_device(idx, q, k, lo)
 
     def e2e_step():
         if world == 1:

@@ -109,6 +109,25 @@ int om_index_reset(om_index* idx);
  * re-scored in fp32).  Synchronous with respect to `stream` on return. */
 int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
                     om_memkind out_kind, int64_t id_offset, void* stream);
+/* Three-phase variant for row-sharded indexes (one shard per process, at most 16384 queries per round trip).
+ * Replaces the per-shard full top-k that faiss IndexShards computes before merging (dense_retriever.py:43-58):
+ * the shards agree on a per-query score floor first, so each one re-scores and ships ~k / n_shards rows.
+ *   begin : bf16 scan of the local shard.  local_range (device fp32 [2, nq]) receives per query the local
+ *           (k + slack)-th best bf16-stage score (row 0; -inf when the shard has fewer rows) and the local best
+ *           (row 1).  The caller MAX-reduces it over the shards.
+ *   count : local_hist (device int32 [nq, om_search_floor_bins()]) receives the histogram of the local
+ *           candidates over equal-width bins of [global_range[0][q], global_range[1][q]].  The caller SUM-reduces.
+ *   finish: re-scores in fp32 only the local candidates in or above the bin holding the global (k + slack)-th
+ *           score (every member of the global top-k is among them) and writes them sorted to device D fp32
+ *           [nq, k] / I int64 [nq, k], padded with -FLT_MAX / -1.  global_hist == NULL: floor = global_range[0];
+ *           global_range == NULL: no pruning.  kept_max (device int32, nullable) receives the longest valid prefix
+ *           over the queries, so the caller can exchange [nq, kept_max] instead of [nq, k]. */
+int om_index_search_begin(om_index* idx, const void* q, om_memkind q_kind, int nq, int k, float* local_range,
+                          void* stream);
+int om_index_search_count(om_index* idx, const float* global_range, int* local_hist, void* stream);
+int om_index_search_finish(om_index* idx, const float* global_range, const int* global_hist, float* D, int64_t* I,
+                           int64_t id_offset, int* kept_max, void* stream);
+int om_search_floor_bins(void);
 /* Tunables: "rescore_slack" (extra bf16-stage candidates kept per query; default max(64, k/8)),
  * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing),
  * "round_growth" (2..8, default 2: each scan round covers (g-1) x the rows already seen),
@@ -125,6 +144,9 @@ void om_index_destroy(om_index* idx);
  * ids < 0 are padding.  Matches merge semantics of faiss IndexShards / utils.py:215-229. */
 int om_topk_merge(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k, float* D, int64_t* I,
                   void* stream);
+/* Same with input lists of width k_in (e.g. the kept_max prefix of om_index_search_finish) and k_out results. */
+int om_topk_merge_n(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k_in, int k_out, float* D,
+                    int64_t* I, void* stream);
 
 /* ---- loss: replaces matmul + cross_entropy + autograd backward ------------------------------------ */
 /* Q [nq, d], P [np, d] device, fp32 or bf16 (both the same dtype), row-major.

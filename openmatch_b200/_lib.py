@@ -47,10 +47,15 @@ SIGNATURES = {
     "om_index_reset": (c_int, [c_void_p]),
     "om_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int64,
                                 c_void_p]),
+    "om_index_search_begin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "om_index_search_count": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "om_index_search_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "om_search_floor_bins": (c_int, []),
     "om_index_set_param": (c_int, [c_void_p, c_char_p, c_int64]),
     "om_index_get_stat": (c_int64, [c_void_p, c_char_p]),
     "om_index_destroy": (None, [c_void_p]),
     "om_topk_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "om_topk_merge_n": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "om_contrastive_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
   extern __shared__ unsigned long long skeys[];
   __shared__ int hist[2048];
   __shared__ unsigned long long s_prefix;
-  __shared__ int s_remaining, s_out, s_bin_count;
+  __shared__ int s_remaining, s_out, s_bin_count, s_wsum[8];
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   unsigned long long* mine = cand + static_cast<size_t>(q) * C;
   int cnt = cnt_override >= 0 ? cnt_override : count[q];
@@ -101,24 +101,30 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
       if (live && lane == (__ffs(peers) - 1)) atomicAdd(&hist[digit], __popc(peers));
     }
     __syncthreads();
-    if (tid < 32) {
-      // lane l owns the bins [nbins - (l+1)*per, nbins - l*per) scanned from the top; find the bin where the
-      // running count from the top reaches `remaining`
-      const int per = nbins >> 5;
+    {
+      // Block-wide scan from the top bin down: thread t owns the `per` consecutive bins at positions
+      // [t * per, (t + 1) * per) counted from the top (read in a per-lane rotated order so the 32 lanes hit 32
+      // banks); find the bin where the running count reaches `remaining`.
+      const int per = nbins >> 8;  // 8, 4 or 1
+      const int remaining = s_remaining;
+      const int rot = per > 1 ? lane / (32 / per) : 0;
       int sum = 0;
-      for (int j = 0; j < per; ++j) sum += hist[nbins - 1 - (lane * per + j)];
+      for (int j = 0; j < per; ++j) sum += hist[nbins - 1 - (tid * per + ((j + rot) & (per - 1)))];
       int incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      const int excl = incl - sum, remaining = s_remaining;
-      __syncwarp();
-      if (excl < remaining && remaining <= incl) {  // exactly one lane
+      if (lane == 31) s_wsum[tid >> 5] = incl;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < (tid >> 5); ++w) base += s_wsum[w];
+      const int excl = base + incl - sum;
+      if (excl < remaining && remaining <= excl + sum) {  // exactly one thread
         int run = excl;
         for (int j = 0; j < per; ++j) {
-          const int bin = nbins - 1 - (lane * per + j), c = hist[bin];
+          const int bin = nbins - 1 - (tid * per + j), c = hist[bin];
           if (run < remaining && remaining <= run + c) {
             s_prefix = prefix | (static_cast<unsigned long long>(bin) << shift);
             s_remaining = remaining - run;
@@ -136,9 +142,14 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
   // keys >= kth under `mask` (keys are unique, so with all 64 bits resolved exactly kp keys qualify; with only
   // the score bits resolved the whole tie group qualifies and it fits by the check above)
   const unsigned long long kth = s_prefix;
-  for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
+  for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {  // compaction, one shared-memory atomic per warp
     const int i = i0 + tid;
-    if (i < cnt && (skeys[i] & mask) >= kth) mine[atomicAdd(&s_out, 1)] = skeys[i];
+    const bool keep = i < cnt && (skeys[i] & mask) >= kth;
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(&s_out, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) mine[base + __popc(b & ((1u << lane) - 1u))] = skeys[i];
   }
   if (tid == 0) {
     count[q] = kp;
@@ -146,11 +157,32 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
   }
 }
 
+// Equal-width score bins shared by every shard of a sharded search (same inputs -> same bin on every rank).
+constexpr int kFloorBins = 256;
+struct FloorBins {
+  float lo, scale;  // bin = floor((s - lo) * scale), clamped to [0, kFloorBins - 1]; s < lo -> -1
+  __device__ static FloorBins make(float lo, float hi) {
+    FloorBins f;
+    f.lo = lo;
+    const float w = hi - lo;
+    f.scale = (w > 0.f && w < 3.0e38f) ? static_cast<float>(kFloorBins) / w : 0.f;  // lo = -inf / hi <= lo: one bin
+    return f;
+  }
+  __device__ int bin(float s) const {
+    if (s < lo) return -1;
+    if (!(scale > 0.f)) return 0;
+    const float t = (s - lo) * scale;
+    return t >= static_cast<float>(kFloorBins - 1) ? kFloorBins - 1 : static_cast<int>(t);
+  }
+};
+
 // FINAL: one CTA per query: exact fp32 re-score of the surviving candidates against the master rows,
 // sort by (score desc, row asc), emit top-k.
 __global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long* cand, const int* count, int C,
                                                        const float* __restrict__ qf, const float* __restrict__ xf,
-                                                       int d, int k, float* D, int64_t* I, int64_t id_offset) {
+                                                       int d, int k, float* D, int64_t* I, int64_t id_offset,
+                                                       const float* __restrict__ range, const int* __restrict__ ghist,
+                                                       int nq_total, int kp, int* kept_max) {
   extern __shared__ unsigned long long fsm[];
   const int q = blockIdx.x;
   int cnt = count[q];
@@ -159,11 +191,49 @@ __global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long*
   unsigned long long* skeys = fsm;
   float* sq = reinterpret_cast<float*>(fsm + P);
   for (int i = threadIdx.x; i < d; i += blockDim.x) sq[i] = qf[static_cast<size_t>(q) * d + i];
-  for (int i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = 0ull;
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const unsigned long long* mine = cand + static_cast<size_t>(q) * C;
+  // sharded search: only candidates in or above the histogram bin that holds the global kp-th bf16-stage score
+  // can be in the global top-k; the others are not re-scored
+  __shared__ int s_minbin;
+  __shared__ int s_n;
+  FloorBins fb{__int_as_float(0xff800000), 0.f};
+  if (range) fb = FloorBins::make(range[q], range[nq_total + q]);
+  if (threadIdx.x == 0) {
+    s_minbin = 0;
+    s_n = 0;
+  }
+  __syncthreads();
+  if (range && ghist && warp == 0) {
+    // lowest bin b with count(bins >= b) >= kp: lane l owns bins [l * per, (l + 1) * per); suffix sums over lanes
+    constexpr int per = kFloorBins / 32;
+    int h[per], sum = 0;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+      h[j] = ghist[static_cast<size_t>(q) * kFloorBins + lane * per + j];
+      sum += h[j];
+    }
+    int suffix = sum;  // sum over lanes >= this one
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, suffix, o);
+      if (lane + o < 32) suffix += v;
+    }
+    int run = suffix - sum;  // count in the bins above this lane's
+    if (run < kp && kp <= suffix) {  // at most one lane; none if the lists hold fewer than kp rows (no pruning)
+      int b = per - 1;
+#pragma unroll
+      for (int j = per - 1; j >= 0; --j) {
+        if (run < kp) b = j;
+        run += h[j];
+      }
+      s_minbin = lane * per + b;
+    }
+  }
+  __syncthreads();
+  const int minbin = s_minbin;
   for (int j = warp; j < cnt; j += nw) {
+    if (range && fb.bin(key_score(mine[j])) < minbin) continue;
     const uint32_t row = key_row(mine[j]);
     const float* x = xf + static_cast<size_t>(row) * d;
     float acc = 0.f;
@@ -182,19 +252,65 @@ __global__ void __launch_bounds__(256) finalize_kernel(const unsigned long long*
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) skeys[j] = make_key(acc, row);
+    if (lane == 0) skeys[atomicAdd(&s_n, 1)] = make_key(acc, row);  // compacted: the sort covers survivors only
   }
   __syncthreads();
-  bitonic_sort_desc(skeys, P, threadIdx.x, blockDim.x);
+  const int n = s_n;
+  int P2 = 2;
+  while (P2 < n) P2 <<= 1;
+  for (int i = n + threadIdx.x; i < P2; i += blockDim.x) skeys[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(skeys, P2, threadIdx.x, blockDim.x);
   for (int r = threadIdx.x; r < k; r += blockDim.x) {
     float s = -FLT_MAX;
     int64_t id = -1;
-    if (r < cnt) {
+    if (r < n) {
       s = key_score(skeys[r]);
       id = id_offset + static_cast<int64_t>(key_row(skeys[r]));
     }
     D[static_cast<size_t>(q) * k + r] = s;
     I[static_cast<size_t>(q) * k + r] = id;
+  }
+  // longest valid prefix over the queries: lets the caller exchange [nq, kept] instead of [nq, k]
+  if (kept_max && threadIdx.x == 0 && n > 0) atomicMax(kept_max, n < k ? n : k);
+}
+
+// COUNT (sharded search): histogram of this shard's surviving candidates over kFloorBins equal-width score bins
+// spanning [range[0][q], range[1][q]] = (best local floor, best local score) over the shards.
+__global__ void __launch_bounds__(256) floor_hist_kernel(const unsigned long long* cand, const int* count, int C,
+                                                         const float* __restrict__ range, int nq, int* hist) {
+  __shared__ int sh[kFloorBins];
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < kFloorBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const FloorBins fb = FloorBins::make(range[q], range[nq + q]);
+  const int cnt = count[q];
+  const unsigned long long* mine = cand + static_cast<size_t>(q) * C;
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+    const int b = fb.bin(key_score(mine[j]));
+    if (b >= 0) atomicAdd(&sh[b], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kFloorBins; i += blockDim.x) hist[static_cast<size_t>(q) * kFloorBins + i] = sh[i];
+}
+
+// per query: {kp-th (floor) and best bf16-stage score} of this shard's candidate list -> range[0][q], range[1][q]
+__global__ void __launch_bounds__(256) local_range_kernel(const unsigned long long* cand, const int* count,
+                                                          const float* thr, int C, int nq, float* range) {
+  __shared__ float smax[8];
+  const int q = blockIdx.x;
+  const int cnt = count[q];
+  const unsigned long long* mine = cand + static_cast<size_t>(q) * C;
+  float m = __int_as_float(0xff800000);
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) m = fmaxf(m, key_score(mine[j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, smax[i]);
+    range[q] = thr[q];
+    range[nq + q] = m;
   }
 }
 
@@ -222,7 +338,7 @@ __global__ void fill_i32(int* p, int v, int n) {
 
 // MERGE (sharded search exchange step): one CTA per query over nparts * k candidates.
 __global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64_t* Ip, int nparts, int nq, int k,
-                                                    float* D, int64_t* I) {
+                                                    int k_out, float* D, int64_t* I) {
   // keys: orderable(score) << 32 | ~slot, with ties broken by id through a second pass on equal scores
   extern __shared__ unsigned long long msm[];
   const int q = blockIdx.x;
@@ -246,7 +362,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64
   bitonic_sort_desc(skeys, P, threadIdx.x, blockDim.x);
   // Shards hold disjoint, increasing id ranges and each shard list is already (score desc, id asc), so slot
   // order == id order among equal scores: the (score, slot) sort is the (score, id) sort.
-  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+  for (int r = threadIdx.x; r < k_out; r += blockDim.x) {
     const unsigned long long key = r < P ? skeys[r] : 0ull;
     float s = -FLT_MAX;
     int64_t id = -1;
@@ -254,8 +370,8 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64
       s = f32_from_orderable(static_cast<uint32_t>(key >> 32));
       id = sid[0xffffffffu - static_cast<uint32_t>(key & 0xffffffffull)];
     }
-    D[static_cast<size_t>(q) * k + r] = s;
-    I[static_cast<size_t>(q) * k + r] = id;
+    D[static_cast<size_t>(q) * k_out + r] = s;
+    I[static_cast<size_t>(q) * k_out + r] = id;
   }
 }
 
@@ -285,6 +401,12 @@ struct om_index {
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // state between om_index_search_begin and om_index_search_finish
+  struct Plan {
+    bool valid = false;
+    int nq = 0, k = 0, kp = 0, kp_target = 0, C = 0, growth = 2;  // kp = min(kp_target = k + slack, rows)
+    size_t o_qf = 0, o_qb = 0, o_cand = 0, o_count = 0, o_thr = 0, o_ovf = 0, o_D = 0, o_I = 0;
+  } plan;
 };
 
 static int index_grow(om_index* ix, int64_t need) {
@@ -547,6 +669,133 @@ int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, int grow
 
 }  // namespace
 
+namespace {
+
+constexpr int kQueryChunk = 16384;
+
+ChunkWs plan_ws(om_index* ix) {
+  uint8_t* base = static_cast<uint8_t*>(ix->ws);
+  const om_index::Plan& p = ix->plan;
+  return ChunkWs{reinterpret_cast<unsigned long long*>(base + p.o_cand), reinterpret_cast<int*>(base + p.o_count),
+                 reinterpret_cast<float*>(base + p.o_thr), reinterpret_cast<int*>(base + p.o_ovf)};
+}
+
+// sizes the candidate lists, carves the workspace and uploads / converts the queries
+int search_prepare(om_index* ix, const void* q, om_memkind q_kind, int nq, int k, bool host_out, cudaStream_t st) {
+  const int d = ix->d, dpad = ix->dpad;
+  if (d > 16384) return fail(OM_EINVAL, "om_index_search: d > 16384 unsupported");
+  int64_t slack = ix->rescore_slack >= 0 ? ix->rescore_slack : std::max<int64_t>(64, k / 8);
+  const int64_t kp64 = std::min<int64_t>(static_cast<int64_t>(k) + slack, std::max<int64_t>(ix->n, 1));
+  if (kp64 > 4096) return fail(OM_EINVAL, "om_index_search: k + slack = %lld exceeds 4096", (long long)kp64);
+  om_index::Plan& p = ix->plan;
+  p.valid = false;
+  p.nq = nq;
+  p.k = k;
+  p.kp = static_cast<int>(kp64);
+  p.kp_target = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(k) + slack, 4096));
+  // Expected list length after a round that multiplies the rows seen by g is ~g kp (kp kept + ~(g-1) kp new
+  // survivors); 25 % + 512 entries of head-room cover its spread for exchangeable row order.
+  for (p.growth = ix->growth;; --p.growth) {  // large k: slower-growing schedule that fits the 16384-entry select
+    p.C = 1024;
+    while (p.C < (5 * p.growth * p.kp) / 4 + 512) p.C <<= 1;
+    if (p.C <= 16384 || p.growth == 2) break;
+  }
+  if (p.C > 16384) return fail(OM_EINVAL, "om_index_search: candidate list of %d entries exceeds 16384; lower k", p.C);
+  ix->st_capacity = p.C;
+  ix->st_rounds = 0;
+  ix->st_retries = 0;
+  ix->st_launches = 1;  // the query fp32 -> bf16 conversion below
+  ix->st_scan_us = ix->st_select_us = ix->st_final_us = 0;
+  ix->ev_used = 0;
+  const int nqc_max = std::min(nq, kQueryChunk);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off += round_up(bytes, 256);
+    return o;
+  };
+  p.o_qf = carve(static_cast<size_t>(nq) * d * 4);
+  p.o_qb = carve(static_cast<size_t>(nq) * dpad * 2);
+  p.o_cand = carve(static_cast<size_t>(nqc_max) * p.C * 8);
+  p.o_count = carve(static_cast<size_t>(nqc_max) * 4);
+  p.o_thr = carve(static_cast<size_t>(nqc_max) * 4);
+  p.o_ovf = carve(256);
+  p.o_D = carve(host_out ? static_cast<size_t>(nq) * k * 4 : 0);
+  p.o_I = carve(host_out ? static_cast<size_t>(nq) * k * 8 : 0);
+  OM_TRY(ws_reserve(ix, off));
+  uint8_t* base = static_cast<uint8_t*>(ix->ws);
+  float* qf = reinterpret_cast<float*>(base + p.o_qf);
+  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(base + p.o_qb);
+  OM_CUDA(cudaMemcpyAsync(qf, q, static_cast<size_t>(nq) * d * 4,
+                          q_kind == OM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  f32_to_bf16_rows<<<grid_for(static_cast<int64_t>(nq) * dpad, 256), 256, 0, st>>>(qf, qb, nq, d, dpad);
+  OM_CUDA(cudaGetLastError());
+  static bool fin_attr = false;
+  if (!fin_attr) {
+    OM_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 8 + 65536));
+    fin_attr = true;
+  }
+  return 0;
+}
+
+// bf16 scan sweep of the shard for queries [q0, q0 + nqc), with the overflow check and the safe-schedule retry
+int search_sweep_checked(om_index* ix, int q0, int nqc, int sms, cudaStream_t st) {
+  const om_index::Plan& p = ix->plan;
+  const ChunkWs w = plan_ws(ix);
+  const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(static_cast<uint8_t*>(ix->ws) + p.o_qb);
+  if (ix->n == 0) {
+    fill_i32<<<(nqc + 255) / 256, 256, 0, st>>>(w.count, 0, nqc);
+    OM_CUDA(cudaGetLastError());
+    return 0;
+  }
+  bool safe = ix->force_safe != 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    OM_TRY(sweep(ix, qb + static_cast<size_t>(q0) * ix->dpad, nqc, p.kp, p.C, p.growth, w, safe, sms, st));
+    int ovf = 0;
+    OM_CUDA(cudaMemcpyAsync(&ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OM_CUDA(cudaStreamSynchronize(st));
+    const unsigned int fault = read_clear_dev_fault();
+    if (fault) return fail(OM_EFAULT, "scan kernel pipeline fault 0x%08x", fault);
+    if (!ovf) return 0;
+    if (safe) return fail(OM_EFAULT, "candidate list overflow in the overflow-proof schedule (bug)");
+    safe = true;
+    ix->st_retries++;
+  }
+  return 0;
+}
+
+int search_finalize(om_index* ix, int q0, int nqc, float* dD, int64_t* dI, int64_t id_offset, const float* range,
+                    const int* ghist, int* kept_max, cudaStream_t st) {
+  const om_index::Plan& p = ix->plan;
+  const ChunkWs w = plan_ws(ix);
+  const float* qf = reinterpret_cast<const float*>(static_cast<uint8_t*>(ix->ws) + p.o_qf);
+  int P2 = 2;
+  while (P2 < p.kp) P2 <<= 1;
+  const size_t fin_smem = static_cast<size_t>(P2) * 8 + static_cast<size_t>(ix->d) * 4;
+  {
+    Timed t(ix, st, 2);
+    finalize_kernel<<<nqc, 256, fin_smem, st>>>(w.cand, w.count, p.C, qf + static_cast<size_t>(q0) * ix->d, ix->xf, ix->d,
+                                                p.k, dD + static_cast<size_t>(q0) * p.k, dI + static_cast<size_t>(q0) * p.k,
+                                                id_offset, range, ghist, p.nq, p.kp_target, kept_max);
+  }
+  OM_CUDA(cudaGetLastError());
+  ix->st_launches += 1;
+  return 0;
+}
+
+int search_emit(om_index* ix, float* D, int64_t* I, float* dD, int64_t* dI, om_memkind out_kind, cudaStream_t st) {
+  const om_index::Plan& p = ix->plan;
+  if (out_kind == OM_HOST) {
+    OM_CUDA(cudaMemcpyAsync(D, dD, static_cast<size_t>(p.nq) * p.k * 4, cudaMemcpyDeviceToHost, st));
+    OM_CUDA(cudaMemcpyAsync(I, dI, static_cast<size_t>(p.nq) * p.k * 8, cudaMemcpyDeviceToHost, st));
+  }
+  OM_CUDA(cudaStreamSynchronize(st));
+  if (ix->profile) collect_profile(ix);
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
                                om_memkind out_kind, int64_t id_offset, void* stream) {
   if (!ix || (nq > 0 && (!q || !D || !I)) || nq < 0 || k <= 0)
@@ -555,115 +804,71 @@ extern "C" int om_index_search(om_index* ix, const void* q, om_memkind q_kind, i
   const int sms = device_sm_count();
   if (sms < 0) return sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int d = ix->d, dpad = ix->dpad;
-  int64_t slack = ix->rescore_slack >= 0 ? ix->rescore_slack : std::max<int64_t>(64, k / 8);
-  const int64_t kp64 = std::min<int64_t>(static_cast<int64_t>(k) + slack, std::max<int64_t>(ix->n, 1));
-  if (kp64 > 4096) return fail(OM_EINVAL, "om_index_search: k + slack = %lld exceeds 4096", (long long)kp64);
-  const int kp = static_cast<int>(kp64);
-  // Expected list length after a round that multiplies the rows seen by g is ~g kp (kp kept + ~(g-1) kp new
-  // survivors); 25 % + 512 entries of head-room cover its spread for exchangeable row order.
-  int growth = ix->growth, C = 0;
-  for (;; --growth) {  // large k: fall back to a slower-growing schedule that fits the 16384-entry select
-    C = 1024;
-    while (C < (5 * growth * kp) / 4 + 512) C <<= 1;
-    if (C <= 16384 || growth == 2) break;
-  }
-  if (C > 16384) return fail(OM_EINVAL, "om_index_search: candidate list of %d entries exceeds 16384; lower k", C);
-  ix->st_capacity = C;
-  ix->st_rounds = 0;
-  ix->st_retries = 0;
-  ix->st_launches = 1;  // the query fp32 -> bf16 conversion below
-  ix->st_scan_us = ix->st_select_us = ix->st_final_us = 0;
-  ix->ev_used = 0;
-
-  const int QCHUNK = 16384;
-  const int nqc_max = std::min(nq, QCHUNK);
-  // workspace layout
-  size_t off = 0;
-  auto carve = [&](size_t bytes) {
-    size_t o = off;
-    off += round_up(bytes, 256);
-    return o;
-  };
-  const size_t o_qf = carve(static_cast<size_t>(nq) * d * 4);
-  const size_t o_qb = carve(static_cast<size_t>(nq) * dpad * 2);
-  const size_t o_cand = carve(static_cast<size_t>(nqc_max) * C * 8);
-  const size_t o_count = carve(static_cast<size_t>(nqc_max) * 4);
-  const size_t o_thr = carve(static_cast<size_t>(nqc_max) * 4);
-  const size_t o_ovf = carve(256);
-  const size_t o_D = carve(out_kind == OM_HOST ? static_cast<size_t>(nq) * k * 4 : 0);
-  const size_t o_I = carve(out_kind == OM_HOST ? static_cast<size_t>(nq) * k * 8 : 0);
-  OM_TRY(ws_reserve(ix, off));
+  OM_TRY(search_prepare(ix, q, q_kind, nq, k, out_kind == OM_HOST, st));
   uint8_t* base = static_cast<uint8_t*>(ix->ws);
-  float* qf = reinterpret_cast<float*>(base + o_qf);
-  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(base + o_qb);
-  ChunkWs w{reinterpret_cast<unsigned long long*>(base + o_cand), reinterpret_cast<int*>(base + o_count),
-            reinterpret_cast<float*>(base + o_thr), reinterpret_cast<int*>(base + o_ovf)};
-  float* dD = out_kind == OM_HOST ? reinterpret_cast<float*>(base + o_D) : D;
-  int64_t* dI = out_kind == OM_HOST ? reinterpret_cast<int64_t*>(base + o_I) : I;
+  float* dD = out_kind == OM_HOST ? reinterpret_cast<float*>(base + ix->plan.o_D) : D;
+  int64_t* dI = out_kind == OM_HOST ? reinterpret_cast<int64_t*>(base + ix->plan.o_I) : I;
+  for (int q0 = 0; q0 < nq; q0 += kQueryChunk) {
+    const int nqc = std::min(kQueryChunk, nq - q0);
+    OM_TRY(search_sweep_checked(ix, q0, nqc, sms, st));
+    OM_TRY(search_finalize(ix, q0, nqc, dD, dI, id_offset, nullptr, nullptr, nullptr, st));
+  }
+  return search_emit(ix, D, I, dD, dI, out_kind, st);
+}
 
-  OM_CUDA(cudaMemcpyAsync(qf, q, static_cast<size_t>(nq) * d * 4,
-                          q_kind == OM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
-  f32_to_bf16_rows<<<grid_for(static_cast<int64_t>(nq) * dpad, 256), 256, 0, st>>>(qf, qb, nq, d, dpad);
+// Three-phase search for row-sharded indexes (one shard per process); see include/openmatch_b200.h.
+extern "C" int om_index_search_begin(om_index* ix, const void* q, om_memkind q_kind, int nq, int k, float* local_range,
+                                     void* stream) {
+  if (!ix || nq <= 0 || !q || !local_range || k <= 0) return fail(OM_EINVAL, "om_index_search_begin: bad arguments");
+  if (nq > kQueryChunk) return fail(OM_EINVAL, "om_index_search_begin: at most %d queries per call", kQueryChunk);
+  const int sms = device_sm_count();
+  if (sms < 0) return sms;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  OM_TRY(search_prepare(ix, q, q_kind, nq, k, false, st));
+  OM_TRY(search_sweep_checked(ix, 0, nq, sms, st));
+  const ChunkWs w = plan_ws(ix);
+  if (ix->n == 0) {
+    fill_i32<<<(nq + 255) / 256, 256, 0, st>>>(reinterpret_cast<int*>(w.thr), static_cast<int>(0xff800000), nq);
+    OM_CUDA(cudaGetLastError());
+  }
+  local_range_kernel<<<nq, 256, 0, st>>>(w.cand, w.count, w.thr, ix->plan.C, nq, local_range);
   OM_CUDA(cudaGetLastError());
-
-  static bool fin_attr = false;
-  if (!fin_attr) {
-    OM_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 8 + 65536));
-    fin_attr = true;
-  }
-  int P2 = 2;
-  while (P2 < kp) P2 <<= 1;
-  const size_t fin_smem = static_cast<size_t>(P2) * 8 + static_cast<size_t>(d) * 4;
-  if (d > 16384) return fail(OM_EINVAL, "om_index_search: d > 16384 unsupported");
-
-  for (int q0 = 0; q0 < nq; q0 += QCHUNK) {
-    const int nqc = std::min(QCHUNK, nq - q0);
-    bool safe = ix->force_safe != 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      if (ix->n == 0) {
-        fill_i32<<<(nqc + 255) / 256, 256, 0, st>>>(w.count, 0, nqc);
-        OM_CUDA(cudaGetLastError());
-      } else {
-        OM_TRY(sweep(ix, qb + static_cast<size_t>(q0) * dpad, nqc, kp, C, growth, w, safe, sms, st));
-      }
-      {
-        Timed t(ix, st, 2);
-        finalize_kernel<<<nqc, 256, fin_smem, st>>>(w.cand, w.count, C, qf + static_cast<size_t>(q0) * d, ix->xf, d, k,
-                                                    dD + static_cast<size_t>(q0) * k, dI + static_cast<size_t>(q0) * k,
-                                                    id_offset);
-      }
-      OM_CUDA(cudaGetLastError());
-      ix->st_launches += 1;
-      int ovf = 0;
-      if (ix->n > 0) {
-        OM_CUDA(cudaMemcpyAsync(&ovf, w.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-        OM_CUDA(cudaStreamSynchronize(st));
-        const unsigned int fault = read_clear_dev_fault();
-        if (fault) return fail(OM_EFAULT, "scan kernel pipeline fault 0x%08x", fault);
-      }
-      if (!ovf) break;
-      if (safe) return fail(OM_EFAULT, "candidate list overflow in the overflow-proof schedule (bug)");
-      safe = true;
-      ix->st_retries++;
-    }
-  }
-  if (out_kind == OM_HOST) {
-    OM_CUDA(cudaMemcpyAsync(D, dD, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
-    OM_CUDA(cudaMemcpyAsync(I, dI, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
-  }
-  OM_CUDA(cudaStreamSynchronize(st));
-  if (ix->profile) collect_profile(ix);
+  ix->st_launches += 1;
+  ix->plan.valid = true;
   return 0;
 }
 
-extern "C" int om_topk_merge(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k, float* D,
-                             int64_t* I, void* stream) {
-  if (nparts <= 0 || nq < 0 || k <= 0 || !D_parts || !I_parts || !D || !I)
+extern "C" int om_index_search_count(om_index* ix, const float* global_range, int* local_hist, void* stream) {
+  if (!ix || !global_range || !local_hist) return fail(OM_EINVAL, "om_index_search_count: bad arguments");
+  if (!ix->plan.valid) return fail(OM_ESTATE, "om_index_search_count: no search in progress (call om_index_search_begin)");
+  const ChunkWs w = plan_ws(ix);
+  floor_hist_kernel<<<ix->plan.nq, 256, 0, static_cast<cudaStream_t>(stream)>>>(w.cand, w.count, ix->plan.C, global_range,
+                                                                             ix->plan.nq, local_hist);
+  OM_CUDA(cudaGetLastError());
+  ix->st_launches += 1;
+  return 0;
+}
+
+extern "C" int om_index_search_finish(om_index* ix, const float* global_range, const int* global_hist, float* D,
+                                      int64_t* I, int64_t id_offset, int* kept_max, void* stream) {
+  if (!ix || !D || !I || (global_hist && !global_range)) return fail(OM_EINVAL, "om_index_search_finish: bad arguments");
+  if (!ix->plan.valid) return fail(OM_ESTATE, "om_index_search_finish: no search in progress (call om_index_search_begin)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ix->plan.valid = false;
+  if (kept_max) OM_CUDA(cudaMemsetAsync(kept_max, 0, sizeof(int), st));
+  OM_TRY(search_finalize(ix, 0, ix->plan.nq, D, I, id_offset, global_range, global_hist, kept_max, st));
+  return search_emit(ix, D, I, D, I, OM_DEVICE, st);
+}
+
+extern "C" int om_search_floor_bins(void) { return kFloorBins; }
+
+extern "C" int om_topk_merge_n(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k_in, int k_out,
+                               float* D, int64_t* I, void* stream) {
+  if (nparts <= 0 || nq < 0 || k_in <= 0 || k_out <= 0 || !D_parts || !I_parts || !D || !I)
     return fail(OM_EINVAL, "om_topk_merge: bad arguments");
   if (nq == 0) return 0;
   OM_TRY(device_sm_count());
-  const int64_t total = static_cast<int64_t>(nparts) * k;
+  const int64_t total = static_cast<int64_t>(nparts) * k_in;
   if (total > 8192) return fail(OM_EINVAL, "om_topk_merge: nparts * k = %lld exceeds 8192", (long long)total);
   int P = 2;
   while (P < total) P <<= 1;
@@ -673,7 +878,12 @@ extern "C" int om_topk_merge(const float* D_parts, const int64_t* I_parts, int n
     OM_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
     attr = true;
   }
-  merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(D_parts, I_parts, nparts, nq, k, D, I);
+  merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(D_parts, I_parts, nparts, nq, k_in, k_out, D, I);
   OM_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int om_topk_merge(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k, float* D,
+                             int64_t* I, void* stream) {
+  return om_topk_merge_n(D_parts, I_parts, nparts, nq, k, k, D, I, stream);
 }

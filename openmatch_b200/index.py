@@ -88,6 +88,39 @@ class FlatIPIndex:
                                              I.data_ptr(), _lib.OM_DEVICE, int(id_offset), _stream()))
         return D, I
 
+    def search_begin(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        """Phase 1 of the sharded search: bf16 scan of the local shard; returns the per-query (local floor, local
+        best) bf16-stage scores as a CUDA fp32 [2, nq] tensor, to be MAX-reduced over the shards."""
+        q = q.contiguous().float()
+        self._check_shape(q.shape)
+        rng = torch.empty((2, q.shape[0]), dtype=torch.float32, device=q.device)
+        _lib.check(self._lib.om_index_search_begin(self._h, q.data_ptr(), _lib.OM_DEVICE, q.shape[0], int(k),
+                                                   rng.data_ptr(), _stream()))
+        self._pending = (q.shape[0], int(k), q.device)
+        return rng
+
+    def search_count(self, global_range: torch.Tensor) -> torch.Tensor:
+        """Phase 2: histogram (CUDA int32 [nq, bins]) of the local candidates over the reduced score range, to be
+        SUM-reduced over the shards."""
+        nq, _, dev = self._pending
+        hist = torch.empty((nq, self._lib.om_search_floor_bins()), dtype=torch.int32, device=dev)
+        _lib.check(self._lib.om_index_search_count(self._h, global_range.data_ptr(), hist.data_ptr(), _stream()))
+        return hist
+
+    def search_finish(self, global_range: Optional[torch.Tensor], global_hist: Optional[torch.Tensor] = None,
+                      id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Phase 3: fp32 re-score of the local candidates at or above the agreed floor -> (D [nq, k], I [nq, k],
+        kept [1] int32 = longest valid prefix over the queries), all on the device."""
+        nq, k, dev = self._pending
+        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        kept = torch.empty((1,), dtype=torch.int32, device=dev)
+        _lib.check(self._lib.om_index_search_finish(
+            self._h, None if global_range is None else global_range.data_ptr(),
+            None if global_hist is None else global_hist.data_ptr(), D.data_ptr(), I.data_ptr(), int(id_offset),
+            kept.data_ptr(), _stream()))
+        return D, I, kept
+
     def search_pinned(self, q_host: torch.Tensor, k: int, D_host: torch.Tensor, I_host: torch.Tensor,
                       id_offset: int = 0) -> None:
         """Host (pinned) in, host (pinned) out — the end-to-end call the benchmark times."""
@@ -136,17 +169,38 @@ def _wrap_device_f32(ptr: int, shape) -> torch.Tensor:
 
 
 def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[nparts, nq, k] per-shard results (shards in increasing id order) -> global (D, I) [nq, k]."""
+    """[nparts, nq, k_in] per-shard results (shards in increasing id order) -> global (D, I) [nq, k]."""
     lib = _lib.load()
-    nparts, nq, kk = D_parts.shape
-    assert kk == k and I_parts.shape == D_parts.shape
+    nparts, nq, k_in = D_parts.shape
+    assert I_parts.shape == D_parts.shape
     D_parts = D_parts.contiguous().float()
     I_parts = I_parts.contiguous().long()
     D = torch.empty((nq, k), dtype=torch.float32, device=D_parts.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=D_parts.device)
-    _lib.check(lib.om_topk_merge(D_parts.data_ptr(), I_parts.data_ptr(), nparts, nq, k, D.data_ptr(), I.data_ptr(),
-                                 _stream()))
+    _lib.check(lib.om_topk_merge_n(D_parts.data_ptr(), I_parts.data_ptr(), nparts, nq, k_in, k, D.data_ptr(),
+                                   I.data_ptr(), _stream()))
     return D, I
+
+
+def sharded_search_device(index: "FlatIPIndex", q: torch.Tensor, k: int, id_offset: int, group=None):
+    """Row-sharded exact search, this rank's part + the exchange (NCCL over NVLink):
+      1. bf16 scan of the local shard                                    -> (floor, best) per query
+      2. all-reduce MAX [2, nq]; local histogram over the agreed range   -> all-reduce SUM [nq, 64]
+      3. fp32 re-score of the local candidates above the global floor (~k / world rows per query, not k)
+      4. all-reduce MAX of the longest kept prefix; all-gather of the [nq, kept] (score, id) lists; merge kernel.
+    Every rank returns the same global (D, I) [nq, k].  Without a process group: the single-shard call."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or q.shape[0] > 16384:
+        D, I = index.search_device(q, k, id_offset=id_offset)
+        return exchange_and_merge(D, I, k, group)
+    rng = index.search_begin(q, k)
+    dist.all_reduce(rng, op=dist.ReduceOp.MAX, group=group)
+    hist = index.search_count(rng)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    D, I, kept = index.search_finish(rng, hist, id_offset=id_offset)
+    dist.all_reduce(kept, op=dist.ReduceOp.MAX, group=group)
+    kc = min(k, max(32, -(-int(kept.item()) // 32) * 32))
+    return exchange_and_merge(D[:, :kc], I[:, :kc], k, group)
 
 
 def exchange_and_merge(D_local: torch.Tensor, I_local: torch.Tensor, k: int, group=None, merge=None):
@@ -161,7 +215,7 @@ def exchange_and_merge(D_local: torch.Tensor, I_local: torch.Tensor, k: int, gro
     Ip = torch.empty((world,) + tuple(I_local.shape), dtype=I_local.dtype, device=I_local.device)
     dist.all_gather(list(Dp.unbind(0)), D_local.contiguous(), group=group)  # views of one [W, nq, k] buffer
     dist.all_gather(list(Ip.unbind(0)), I_local.contiguous(), group=group)
-    return (merge or merge_topk_device)(Dp, Ip, k)
+    return (merge or merge_topk_device)(Dp, Ip, k)  # input lists may be narrower than k (pruned exchange)
 
 
 def shard_offsets(n_local: int, group=None):
@@ -202,8 +256,7 @@ class ShardedFlatIPIndex:
         return self._ntotal
 
     def search_device(self, q: torch.Tensor, k: int):
-        Dl, Il = self.local.search_device(q, k, id_offset=self.offset)
-        return exchange_and_merge(Dl, Il, k, self.group)
+        return sharded_search_device(self.local, q, k, self.offset, self.group)
 
     def search(self, q, k: int):
         if not isinstance(q, torch.Tensor):

@@ -29,7 +29,7 @@ from tqdm import tqdm
 
 from ..arguments import InferenceArguments as EncodingArguments
 from ..dataset import DRInferenceCollator
-from ..index import FlatIPIndex, exchange_and_merge, shard_offsets
+from ..index import FlatIPIndex, shard_offsets, sharded_search_device
 from ..modeling import DRModelForInference
 from ..utils import merge_retrieval_results_by_score
 
@@ -206,8 +206,7 @@ class Retriever:
             self._initialize_faiss_index(encoded.shape[1])
         offset, _ = shard_offsets(len(self.doc_lookup))
         q = torch.from_numpy(np.ascontiguousarray(encoded, dtype=np.float32)).to(self.args.device)
-        Dl, Il = self.index.search_device(q, topk, id_offset=offset)
-        D, I = exchange_and_merge(Dl, Il, topk)
+        D, I = sharded_search_device(self.index, q, topk, offset)
         lookups = [None] * W if r == 0 else None
         dist.gather_object(self.doc_lookup, lookups, dst=0)
         if r != 0:

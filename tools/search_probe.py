@@ -7,6 +7,7 @@ import time
 
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from openmatch_b200.index import FlatIPIndex
 
 torch.manual_seed(0)
@@ -39,6 +40,8 @@ for N, nq, k in cases:
         print(f"N={N} nq={nq} k={k}: {1e3*(t2-t1):.1f} ms -> {nq/(t2-t1):.0f} q/s  "
               f"rounds={idx.stat('rounds')} retries={idx.stat('overflow_retries')} C={idx.stat('candidates')} "
               f"({2*nq*N*d/(t2-t1)/1e12:.0f} TFLOP/s eff)", flush=True)
+    if os.environ.get("OM_PROFILE"):
+        print("   phases ms: scan %.2f select %.2f finalize %.2f" % tuple(idx.stat(n) / 1e6 for n in ("scan_ns", "select_ns", "finalize_ns")), flush=True)
     nchk = min(nq, 64)
     kth = D[:nchk, k - 1:k]
     above = torch.zeros(nchk, dtype=torch.int64, device="cuda")
