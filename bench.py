@@ -265,6 +265,30 @@ def main():
                                "note": "whole encoder step (22.35 GFLOP/passage algorithmic) / step time; " + peaks["source"]}}
         del enc
 
+    # contrastive loss fwd+bwd (C4): local negatives [64, 768] x [512, 768] and the cross-device-at-8 shape
+    # [512, 768] x [4096, 768]; one cooperative tcgen05 kernel per call (latency-bound: reported in microseconds)
+    loss_obj = None
+    if not args.skip_encode:
+        from openmatch_b200 import _lib as om_lib
+        lib = om_lib.load()
+        loss_obj = {"metric": "contrastive loss fwd+bwd latency", "unit": "us", "kernel_launches_per_call": 1, "shapes": {}}
+        for name, (bq, bp) in {"local_64x512": (64, 512), "xdevice8_512x4096": (512, 4096)}.items():
+            g = torch.Generator(device="cpu").manual_seed(1234)
+            xq = (torch.randn(bq, 768, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+            xp = (torch.randn(bp, 768, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+            lo_t = torch.empty((), dtype=torch.float32, device=dev)
+            dxq, dxp = torch.empty(bq, 768, device=dev), torch.empty(bp, 768, device=dev)
+            reps = 50
+
+            def loss_step():
+                for _ in range(reps):
+                    om_lib.check(lib.om_contrastive_loss_fwd_bwd(
+                        xq.data_ptr(), xp.data_ptr(), om_lib.OM_BF16, bq, bp, 768, None, om_lib.OM_REDUCE_MEAN, 1.0,
+                        lo_t.data_ptr(), dxq.data_ptr(), dxp.data_ptr(), None, om_lib.current_stream_ptr()))
+
+            us = timed(loss_step, 3, 3) / 3 / reps * 1e3
+            loss_obj["shapes"][name] = {"us": us, "tflops": 6.0 * bq * bp * 768 / (us * 1e-6) / 1e12}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,6 +332,8 @@ def main():
     }
     if encode:
         line["encode"] = encode
+    if loss_obj:
+        line["loss"] = loss_obj
     if world == 1 and not args.skip_cpu:
         base = cpu_reference_search(args, 1, 0)
         line["cpu_baseline"] = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}

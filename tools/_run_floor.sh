@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_search_gpu.py tests/test_retriever_gpu.py -x -q 2>&1 | tail -3
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py 2>&1 | tail -1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_n2_floor.json
+timeout 300 python -m pytest tests/test_loss_gpu.py -x -q 2>&1 | tail -5
+timeout 600 python bench.py --steps 3 --warmup 3 --skip-cpu 2>&1 | tail -1 > gpurun_out/bench_loss.json
+python -c "
+import json;d=json.load(open('gpurun_out/bench_loss.json'));print(d['value'],d['ms_per_step'],d['loss'],d['encode']['ms_per_step'])"
