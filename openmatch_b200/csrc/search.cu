@@ -69,10 +69,26 @@ __global__ void __launch_bounds__(256) select_kernel(unsigned long long* cand, i
   unsigned long long* mine = cand + static_cast<size_t>(q) * C;
   int cnt = cnt_override >= 0 ? cnt_override : count[q];
   cnt = cnt < C ? cnt : C;
-  if (cnt <= kp) {  // nothing to drop yet: no threshold
+  if (cnt < kp) {  // nothing to drop yet: no threshold
     if (tid == 0) {
       count[q] = cnt;
       thr[q] = __int_as_float(0xff800000);
+    }
+    return;
+  }
+  if (cnt == kp) {
+    // exactly kp entries (a round without survivors, or a shard of exactly kp rows): the list stays as it is and
+    // the threshold is its smallest key.  (Resetting it to -inf here let the next round accept every row.)
+    unsigned long long m = ~0ull;
+    for (int i = tid; i < cnt; i += blockDim.x) m = min(m, mine[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) skeys[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < static_cast<int>(blockDim.x >> 5); ++i) m = min(m, skeys[i]);
+      count[q] = cnt;
+      thr[q] = key_score(m);
     }
     return;
   }
@@ -296,7 +312,8 @@ __global__ void __launch_bounds__(256) floor_hist_kernel(const unsigned long lon
 
 // per query: {kp-th (floor) and best bf16-stage score} of this shard's candidate list -> range[0][q], range[1][q]
 __global__ void __launch_bounds__(256) local_range_kernel(const unsigned long long* cand, const int* count,
-                                                          const float* thr, int C, int nq, float* range) {
+                                                          const float* thr, int C, int nq, int has_floor,
+                                                          float* range) {
   __shared__ float smax[8];
   const int q = blockIdx.x;
   const int cnt = count[q];
@@ -309,7 +326,7 @@ __global__ void __launch_bounds__(256) local_range_kernel(const unsigned long lo
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; ++i) m = fmaxf(m, smax[i]);
-    range[q] = thr[q];
+    range[q] = has_floor ? thr[q] : __int_as_float(0xff800000);  // a floor needs k + slack local rows
     range[nq + q] = m;
   }
 }
@@ -831,7 +848,8 @@ extern "C" int om_index_search_begin(om_index* ix, const void* q, om_memkind q_k
     fill_i32<<<(nq + 255) / 256, 256, 0, st>>>(reinterpret_cast<int*>(w.thr), static_cast<int>(0xff800000), nq);
     OM_CUDA(cudaGetLastError());
   }
-  local_range_kernel<<<nq, 256, 0, st>>>(w.cand, w.count, w.thr, ix->plan.C, nq, local_range);
+  local_range_kernel<<<nq, 256, 0, st>>>(w.cand, w.count, w.thr, ix->plan.C, nq, ix->n >= ix->plan.kp_target ? 1 : 0,
+                                         local_range);
   OM_CUDA(cudaGetLastError());
   ix->st_launches += 1;
   ix->plan.valid = true;

@@ -182,17 +182,19 @@ def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor, k: int) -> T
     return D, I
 
 
-def sharded_search_device(index: "FlatIPIndex", q: torch.Tensor, k: int, id_offset: int, group=None):
+def sharded_search_device(index: "FlatIPIndex", q: torch.Tensor, k: int, id_offset: int, group=None, merge=None):
     """Row-sharded exact search, this rank's part + the exchange (NCCL over NVLink):
       1. bf16 scan of the local shard                                    -> (floor, best) per query
       2. all-reduce MAX [2, nq]; local histogram over the agreed range   -> all-reduce SUM [nq, 64]
       3. fp32 re-score of the local candidates above the global floor (~k / world rows per query, not k)
       4. all-reduce MAX of the longest kept prefix; all-gather of the [nq, kept] (score, id) lists; merge kernel.
-    Every rank returns the same global (D, I) [nq, k].  Without a process group: the single-shard call."""
+    Every rank returns the same global (D, I) [nq, k].  Without a process group: the single-shard call.
+    ``index`` only needs ``search_begin / search_count / search_finish`` (tests run this function on CPU under
+    gloo with the oracle's restatement of the three phases and the oracle's ``merge``)."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1 or q.shape[0] > 16384:
         D, I = index.search_device(q, k, id_offset=id_offset)
-        return exchange_and_merge(D, I, k, group)
+        return exchange_and_merge(D, I, k, group, merge)
     rng = index.search_begin(q, k)
     dist.all_reduce(rng, op=dist.ReduceOp.MAX, group=group)
     hist = index.search_count(rng)
@@ -200,7 +202,7 @@ def sharded_search_device(index: "FlatIPIndex", q: torch.Tensor, k: int, id_offs
     D, I, kept = index.search_finish(rng, hist, id_offset=id_offset)
     dist.all_reduce(kept, op=dist.ReduceOp.MAX, group=group)
     kc = min(k, max(32, -(-int(kept.item()) // 32) * 32))
-    return exchange_and_merge(D[:, :kc], I[:, :kc], k, group)
+    return exchange_and_merge(D[:, :kc], I[:, :kc], k, group, merge)
 
 
 def exchange_and_merge(D_local: torch.Tensor, I_local: torch.Tensor, k: int, group=None, merge=None):

@@ -13,7 +13,9 @@ Pinning status (see DESIGN.md "Oracle"):
     un-installed dependency of the reference; the reference ships no test or golden vector for it), so for
     the search step parity is anchored on the reference's call sites only: **parity unpinned** w.r.t. faiss.
 """
-from .flat_index import FlatIPIndex, flat_ip_search, merge_topk, merge_retrieval_results_by_score  # noqa: F401
+from .flat_index import (  # noqa: F401
+    FlatIPIndex, ShardPhases, flat_ip_search, merge_topk, merge_retrieval_results_by_score,
+)
 from .loss import contrastive_loss, contrastive_loss_fwd_bwd  # noqa: F401
 from .encoder import (  # noqa: F401
     bert_encode, t5_encode, pool_head_normalize, encode_reps, t5_relative_position_bucket, EncoderSpec,

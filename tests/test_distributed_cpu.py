@@ -42,6 +42,18 @@ def _worker(rank, world, port, tmp):
         D0, I0 = oracle.flat_ip_search(q, x, 25)
         assert (Im.numpy() == I0).all() and (Dm.numpy() == D0).all()
 
+        # the three-phase protocol (range MAX, histogram SUM, pruned re-score, narrow exchange) through the very
+        # function the ranks run on GPUs, with the oracle's restatement of the three kernels
+        from openmatch_b200.index import sharded_search_device
+        for lo_v, hi_v, k in ((-4, 5, 25), (0, 2, 40)):  # second case: heavy score ties
+            xs = rng.integers(lo_v, hi_v, (3000, 32)).astype(np.float32)
+            qs = rng.integers(lo_v, hi_v, (9, 32)).astype(np.float32)
+            b2 = [0, 1700, 3000]
+            shard = oracle.ShardPhases(xs[b2[rank]:b2[rank + 1]], slack=16)
+            Dm, Im = sharded_search_device(shard, torch.from_numpy(qs), k, b2[rank], merge=_oracle_merge)
+            D0, I0 = oracle.flat_ip_search(qs, xs, k)
+            assert (Im.numpy() == I0).all() and (Dm.numpy() == D0).all()
+
         # cross-device negatives: gathered tensor is rank-major and only the local slice carries gradient
         from openmatch_b200.modeling.dense_retrieval_model import DRModel
         m = DRModel.__new__(DRModel)

@@ -95,6 +95,24 @@ def test_sorted_corpus_forces_overflow_retry(om):
     np.testing.assert_array_equal(I, I0)
 
 
+def test_descending_corpus_needs_no_retry(om):
+    # the opposite order: after the first round no later row ever beats the threshold (rounds without survivors);
+    # the threshold must survive such rounds, otherwise the next round accepts every row and overflows
+    n, d = 60000, 64
+    v = (n - 1 - np.arange(n)) // 4
+    base = np.zeros((n, d), np.float32)
+    base[:, 0], base[:, 1] = v // 128, v % 128
+    q = np.zeros((3, d), np.float32)
+    q[:, 0], q[:, 1] = [128, 256, 384], [1, 2, 3]
+    idx = om.FlatIPIndex(d)
+    idx.add(base)
+    D, I = idx.search(q, 100)
+    assert idx.stat("overflow_retries") == 0
+    D0, I0 = oracle.flat_ip_search(q, base, 100)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+
+
 def _eps_check(q, x, D, I, k, rel=2e-5):
     """Every returned (id, score) must be a valid top-k answer up to eps-ties: the float64 score of the
     r-th returned id equals the r-th best float64 score within eps, and the returned fp32 score equals the
@@ -195,6 +213,36 @@ def test_three_phase_sharded_search_prunes_and_stays_exact(om, lo, hi, bounds):
     Dn, In, _ = shards[1].search_finish(None, None, id_offset=bounds[1])
     Dl, Il = shards[1].search_device(qd, k, id_offset=bounds[1])
     assert torch.equal(In, Il) and torch.equal(Dn, Dl)
+
+
+def test_shard_phases_match_oracle_phase_by_phase(om):
+    # integer data: bf16-stage scores are exact, so every intermediate of the protocol must equal the oracle's
+    rng = np.random.default_rng(77)
+    x, q = _int_data(rng, 9000, 64, -4, 4), _int_data(rng, 17, 64, -4, 4)
+    k, bounds = 50, [0, 4000, 9000]
+    qd = torch.from_numpy(q).cuda()
+    cu, cpu = [], []
+    for s in range(2):
+        idx = om.FlatIPIndex(64)
+        idx.add(x[bounds[s]:bounds[s + 1]])
+        cu.append(idx)
+        cpu.append(oracle.ShardPhases(x[bounds[s]:bounds[s + 1]], slack=64))
+    r_cu = [i.search_begin(qd, k) for i in cu]
+    r_cpu = [o.search_begin(torch.from_numpy(q), k) for o in cpu]
+    for a, b in zip(r_cu, r_cpu):
+        assert torch.equal(a.cpu(), b)
+    grange = torch.stack(r_cpu).max(dim=0).values
+    h_cu = [i.search_count(grange.cuda()) for i in cu]
+    h_cpu = [o.search_count(grange) for o in cpu]
+    for a, b in zip(h_cu, h_cpu):
+        assert torch.equal(a.cpu(), b)
+    ghist = (h_cpu[0] + h_cpu[1]).to(torch.int32)
+    for s in range(2):
+        D, I, kept = cu[s].search_finish(grange.cuda(), ghist.cuda(), id_offset=bounds[s])
+        D0, I0, kept0 = cpu[s].search_finish(grange, ghist, id_offset=bounds[s])
+        assert int(kept.item()) == int(kept0.item())
+        np.testing.assert_array_equal(I.cpu().numpy(), I0.numpy())
+        np.testing.assert_array_equal(D.cpu().numpy(), D0.numpy())
 
 
 def test_zero_copy_ingest(om):
