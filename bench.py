@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--encode-batch", type=int, default=256)
     ap.add_argument("--skip-encode", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-train", action="store_true")
     return ap.parse_args()
 
 
@@ -289,6 +290,45 @@ def main():
             us = timed(loss_step, 3, 3) / 3 / reps * 1e3
             loss_obj["shapes"][name] = {"us": us, "tflops": 6.0 * bq * bp * 768 / (us * 1e-6) / 1e12}
 
+    # contrastive training step (C4): bert-base, 64 queries (L=32) x 8 passages (L=128) per GPU, bf16 autocast.
+    # Encoder forward/backward = the HF torch module under autograd (our encoder kernels are forward-only, DESIGN
+    # section 6); loss forward+backward = loss_fused_kernel; AdamW step included; DDP all-reduce when world > 1.
+    train_obj = None
+    if not args.skip_encode and not args.skip_train:
+        try:
+            import types
+            from transformers import BertConfig, BertModel
+            from openmatch_b200.modeling import DRModel
+            torch.manual_seed(0)
+            lm = BertModel(BertConfig(), add_pooling_layer=False).to(dev)
+            model = DRModel(lm, lm, tied=True, pooling="first",
+                            data_args=types.SimpleNamespace(train_n_passages=8),
+                            train_args=types.SimpleNamespace(negatives_x_device=False)).to(dev).train()
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if world > 1 else model
+            opt = torch.optim.AdamW(net.parameters(), lr=5e-6, fused=True)
+            qi, qm = synthetic.token_batch(64, 32, 30522, seed=77 + rank, device=dev)
+            pi, pm = synthetic.token_batch(512, 128, 30522, seed=177 + rank, device=dev)
+            qb_ = {"input_ids": qi, "attention_mask": qm, "token_type_ids": torch.zeros_like(qi)}
+            pb_ = {"input_ids": pi, "attention_mask": pm, "token_type_ids": torch.zeros_like(pi)}
+
+            def train_step():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = net(qb_, pb_).loss
+                loss.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+
+            tr_ms = timed(train_step, 5, 3) / 5
+            flop = 3 * (64 * 12 * 32 * (24 * 768 * 768 + 4 * 32 * 768) + 512 * 12 * 128 * (24 * 768 * 768 + 4 * 128 * 768))
+            train_obj = {"metric": "train queries/sec (bert-base, 64 q x 8 psg per GPU, bf16)", "value": world * 64 / (tr_ms * 1e-3),
+                         "unit": "queries/s", "ms_per_step": tr_ms, "tflops_per_gpu": flop / (tr_ms * 1e-3) / 1e12,
+                         "note": "encoder fwd/bwd: HF torch module under autograd (cuBLAS/SDPA); loss fwd+bwd: "
+                                 "loss_fused_kernel; fused AdamW; DDP all-reduce when n_gpus > 1"}
+            del model, net, opt, lm
+            torch.cuda.empty_cache()
+        except Exception as e:  # informational leg: never take the search line down with it
+            train_obj = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,6 +374,8 @@ def main():
         line["encode"] = encode
     if loss_obj:
         line["loss"] = loss_obj
+    if train_obj:
+        line["train"] = train_obj
     if world == 1 and not args.skip_cpu:
         base = cpu_reference_search(args, 1, 0)
         line["cpu_baseline"] = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
