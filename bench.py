@@ -265,6 +265,23 @@ def main():
                                "unit": "TFLOP/s", "frac": flop / (enc_ms * 1e-3) / 1e12 / peaks["tflops"],
                                "note": "whole encoder step (22.35 GFLOP/passage algorithmic) / step time; " + peaks["source"]}}
         del enc
+        # C3's encoder: t5-base (GTR) + masked mean pooling + bias-free 768x768 head + L2 normalisation
+        try:
+            tspec = dict(synthetic.T5_BASE)
+            tenc = CudaEncoder(tspec, synthetic.t5_state_dict(tspec, seed=0),
+                               head_weight=torch.randn(768, 768, generator=torch.Generator().manual_seed(3)) * 0.03,
+                               pooling="mean", normalize=True, max_batch_tokens=B * L)
+            tids, tmask = synthetic.token_batch(B, L, tspec["vocab"], seed=4321 + rank, bert=False, device=dev)
+
+            def t5_step():
+                tenc.encode(tids, tmask, out=out)
+
+            t5_ms = timed(t5_step, max(args.steps, 5), 3) / max(args.steps, 5)
+            encode["t5_base_gtr"] = {"value": world * B / (t5_ms * 1e-3), "unit": "passages/s", "ms_per_step": t5_ms,
+                                     "frac_of_peak": flop / (t5_ms * 1e-3) / 1e12 / peaks["tflops"]}
+            del tenc
+        except Exception as e:  # informational leg
+            encode["t5_base_gtr"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # contrastive loss fwd+bwd (C4): local negatives [64, 768] x [512, 768] and the cross-device-at-8 shape
     # [512, 768] x [4096, 768]; one cooperative tcgen05 kernel per call (latency-bound: reported in microseconds)

@@ -26,7 +26,8 @@
 namespace om {
 
 constexpr int kHeadDim = 64;
-constexpr int kMaxL = 128;
+constexpr int kMaxL = 128;       // one attention tile; sequences of at most kMaxL tokens take attn_kernel
+constexpr int kMaxLongL = 512;   // longer sequences (multiples of 128 tokens) take attn_long_kernel
 constexpr float kLog2e = 1.4426950408889634f;
 
 // ===================================================================================================
@@ -538,6 +539,189 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sequences longer than one tile (L = 256 / 384 / 512, multiples of 128): one CTA per (128-row query tile, head)
+// loops over the sequence's 128-key tiles with an online softmax:  S_j = Q K_j^T (tcgen05 -> TMEM) -> running
+// max / sum in registers (thread = query row) -> P_j (bf16, swizzled smem) -> O_j = P_j V_j (tcgen05 -> TMEM) ->
+// acc = acc * alpha + O_j in registers.  Q stays in smem; K_j / V_j are re-loaded by TMA per iteration.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kAttnLongSmemQ = 0, kAttnLongSmemK = 16384, kAttnLongSmemV = 32768, kAttnLongSmemP = 49152;
+constexpr int kAttnLongSmemMisc = 81920;  // rel[1024] f32, key bits [4 tiles x 4 words], barriers, tmem slot
+constexpr int kAttnLongTmemCols = 256;    // S_j: columns [0, 128); O_j: columns [128, 192)
+constexpr int kAttnLongSmemBytes = kAttnLongSmemMisc + 4096 + 64 + 64 + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+attn_long_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_rel = reinterpret_cast<float*>(smem + kAttnLongSmemMisc);
+  uint32_t* s_kb = reinterpret_cast<uint32_t*>(s_rel + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kb + 16);  // [0] loads, [1] S ready, [2] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qt = blockIdx.x, head = blockIdx.y;
+  const int nk = p.L / 128;                 // key tiles per sequence
+  const int row0 = qt * 128;                // first token of this query tile
+  const int kt0 = (qt / nk) * nk;           // first tile of the sequence this query tile belongs to
+  const int qpos0 = (qt - kt0) * 128;       // position of the tile's first query inside its sequence
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmVt);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, kAttnLongTmemCols);
+    tmem_relinquish();
+  }
+  for (int j = 0; j < nk; ++j) {  // key validity of every key tile of the sequence: one ballot per warp and tile
+    const int tok = (kt0 + j) * 128 + tid;
+    const bool key_ok = tok < p.T && p.kmask[tok] == 0.f;
+    const unsigned bits = __ballot_sync(0xffffffffu, key_ok);
+    if ((tid & 31) == 0) s_kb[j * 4 + warp] = bits;
+  }
+  if (p.relbias_log2) {
+    for (int i = tid; i < 2 * kMaxLongL - 1; i += 128) s_rel[i] = p.relbias_log2[head * (2 * kMaxLongL - 1) + i];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  const int r = tid;
+  const bool row_valid = row0 + r < p.T;
+  const bool has_rel = p.relbias_log2 != nullptr;
+  const int rel0 = (kMaxLongL - 1) - (qpos0 + r);  // + key position = index into s_rel
+  float m_run = __int_as_float(0xff800000), sum = 0.f;
+  float acc[kHeadDim];
+#pragma unroll
+  for (int i = 0; i < kHeadDim; ++i) acc[i] = 0.f;
+  uint8_t* sP = smem + kAttnLongSmemP;
+
+#pragma unroll 1
+  for (int j = 0; j < nk; ++j) {
+    const uint32_t par = static_cast<uint32_t>(j & 1);
+    if (tid == 0) {
+      // K / V of the previous iteration are dead: S_{j-1} and O_{j-1} have completed (every thread waited on them)
+      mbar_arrive_expect_tx(&bars[0], (j == 0 ? 3 : 2) * 16384);
+      if (j == 0) tma_load_2d(smem + kAttnLongSmemQ, &tmQK, &bars[0], head * kHeadDim, row0);
+      tma_load_2d(smem + kAttnLongSmemK, &tmQK, &bars[0], p.I + head * kHeadDim, (kt0 + j) * 128);
+      tma_load_2d(smem + kAttnLongSmemV, &tmVt, &bars[0], (kt0 + j) * 128, head * kHeadDim);
+      tma_load_2d(smem + kAttnLongSmemV + 8192, &tmVt, &bars[0], (kt0 + j) * 128 + 64, head * kHeadDim);
+      mbar_wait(&bars[0], par, 13);
+      tc_fence_after_sync();
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      const uint32_t qa = smem_u32(smem + kAttnLongSmemQ), ka = smem_u32(smem + kAttnLongSmemK);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_ss(tmem_base, umma_smem_desc(qa + k * 32, kDescKMajorSW128),
+                     umma_smem_desc(ka + k * 32, kDescKMajorSW128), idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&bars[1]);
+    }
+    mbar_wait_warp(&bars[1], par, 14);
+    tc_fence_after_sync();
+
+    // ---- running max over this key tile ----
+    float m_j = __int_as_float(0xff800000);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(taddr + c4 * 32, raw);
+      tmem_ld_wait();
+      const uint32_t aw = row_valid ? s_kb[j * 4 + c4] : 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float sc = __uint_as_float(raw[i]) * p.scale_log2;
+        if (has_rel) sc += s_rel[rel0 + j * 128 + c4 * 32 + i];
+        if (!(aw & (1u << i))) sc = __int_as_float(0xff800000);
+        m_j = fmaxf(m_j, sc);
+      }
+    }
+    const float m_new = fmaxf(m_run, m_j);
+    const bool dead = !(m_new > __int_as_float(0xff800000));  // no allowed key seen so far
+    const float mm = dead ? 0.f : m_new;
+    const float alpha = (m_run > __int_as_float(0xff800000)) ? ex2_approx(m_run - mm) : 0.f;
+    m_run = m_new;
+    sum *= alpha;
+    const float neg_mm = -mm;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(taddr + c4 * 32, raw);
+      tmem_ld_wait();
+      const uint32_t aw = (row_valid && !dead) ? s_kb[j * 4 + c4] : 0u;
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float pv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float sc = fmaf(__uint_as_float(raw[i + u]), p.scale_log2, neg_mm);
+          if (has_rel) sc += s_rel[rel0 + j * 128 + c4 * 32 + i + u];
+          pv[u] = (aw & (1u << (i + u))) ? ex2_approx(sc) : 0.f;
+        }
+        sum += pv[0] + pv[1];
+        packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+      }
+      uint8_t* blk = sP + (c4 >> 1) * 16384 + r * 128;  // K-major SWIZZLE_128B, see attn_kernel
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int chunk = ((c4 & 1) * 4 + q4) ^ (r & 7);
+        *reinterpret_cast<uint4*>(blk + chunk * 16) =
+            make_uint4(packed[4 * q4], packed[4 * q4 + 1], packed[4 * q4 + 2], packed[4 * q4 + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after_sync();
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+      const uint32_t pa = smem_u32(sP), va = smem_u32(smem + kAttnLongSmemV);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16_ss(tmem_base + 128, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, kDescKMajorSW128),
+                     umma_smem_desc(va + (k >> 2) * 8192 + (k & 3) * 32, kDescKMajorSW128), idesc_o, k != 0 ? 1u : 0u);
+      umma_commit(&bars[2]);
+    }
+    mbar_wait_warp(&bars[2], par, 15);
+    tc_fence_after_sync();
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(taddr + 128 + c2 * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[c2 * 32 + i] = fmaf(acc[c2 * 32 + i], alpha, __uint_as_float(raw[i]));
+    }
+    tc_fence_before_sync();  // the next iteration's MMAs overwrite S (after this thread's reads above)
+  }
+
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  if (row_valid) {
+    uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<int64_t>(row0 + r) * p.I + head * kHeadDim);
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = pack_bf16x2(acc[8 * q8 + 2 * u] * inv, acc[8 * q8 + 2 * u + 1] * inv);
+      dst[q8] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kAttnLongTmemCols);
+  }
+}
+
 // ===================================================================================================
 // pooling / head / normalise (fp32)
 // ===================================================================================================
@@ -549,7 +733,7 @@ __global__ void pool_kernel(const float* hidden, const int64_t* mask, int L, int
     for (int c = threadIdx.x; c < H; c += blockDim.x) pooled[static_cast<int64_t>(b) * H + c] = src[c];
     return;
   }
-  __shared__ float sm[kMaxL];
+  __shared__ float sm[kMaxLongL];
   for (int l = threadIdx.x; l < L; l += blockDim.x) sm[l] = mask[static_cast<int64_t>(b) * L + l] != 0 ? 1.f : 0.f;
   __syncthreads();
   float cnt = 0.f;
@@ -648,6 +832,7 @@ struct om_encoder {
   float* rel_w = nullptr;         // T5 [buckets, heads] (host copy kept in rel_host)
   std::vector<float> rel_host;
   float* relbias_log2 = nullptr;  // [heads, 255]
+  float* relbias_long_log2 = nullptr;  // [heads, 1023] (sequences longer than one tile)
   float* head_w = nullptr;        // [head_out, H]
   std::vector<std::string> missing;
   std::vector<std::pair<std::string, bool>> required;  // name -> set?
@@ -754,6 +939,7 @@ int om_encoder_create(const om_encoder_desc* desc, om_encoder** out) {
     A(&e->final_g, H);
     A(&e->rel_w, (size_t)d.rel_buckets * d.heads);
     A(&e->relbias_log2, (size_t)d.heads * (2 * kMaxL - 1));
+    A(&e->relbias_long_log2, (size_t)d.heads * (2 * kMaxLongL - 1));
     require(e, "shared.weight");
     require(e, "encoder.final_layer_norm.weight");
     require(e, "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight");
@@ -967,17 +1153,22 @@ int om_encoder_finalize(om_encoder* e) {
     }
   if (nmiss) return fail(OM_ESTATE, "om_encoder_finalize: %d parameter(s) missing: %s%s", nmiss, miss.c_str(), nmiss > 4 ? ", ..." : "");
   if (e->d.arch == OM_ARCH_T5ENC) {
-    const int nh = e->d.heads, W = 2 * kMaxL - 1;
-    std::vector<float> table((size_t)nh * W);
-    for (int rel = -(kMaxL - 1); rel <= kMaxL - 1; ++rel) {
-      const int b = t5_bucket(rel, e->d.rel_buckets, e->d.rel_max_distance);
-      for (int h = 0; h < nh; ++h) table[(size_t)h * W + rel + kMaxL - 1] = e->rel_host[(size_t)b * nh + h] * kLog2e;
+    const int nh = e->d.heads;
+    for (int pass = 0; pass < 2; ++pass) {  // one table per attention kernel
+      const int maxl = pass == 0 ? kMaxL : kMaxLongL, W = 2 * maxl - 1;
+      std::vector<float> table((size_t)nh * W);
+      for (int rel = -(maxl - 1); rel <= maxl - 1; ++rel) {
+        const int b = t5_bucket(rel, e->d.rel_buckets, e->d.rel_max_distance);
+        for (int h = 0; h < nh; ++h) table[(size_t)h * W + rel + maxl - 1] = e->rel_host[(size_t)b * nh + h] * kLog2e;
+      }
+      OM_CUDA(cudaMemcpy(pass == 0 ? e->relbias_log2 : e->relbias_long_log2, table.data(), table.size() * 4,
+                         cudaMemcpyHostToDevice));
     }
-    OM_CUDA(cudaMemcpy(e->relbias_log2, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
   }
   static bool attr = false;
   if (!attr) {
     OM_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    OM_CUDA(cudaFuncSetAttribute(attn_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnLongSmemBytes));
     attr = true;
   }
   e->finalized = true;
@@ -989,7 +1180,10 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
   if (!e || !input_ids || !attention_mask || !out_reps) return fail(OM_EINVAL, "om_encode: null argument");
   if (!e->finalized) return fail(OM_ESTATE, "om_encode: call om_encoder_finalize first");
   if (B <= 0 || L <= 0) return fail(OM_EINVAL, "om_encode: B and L must be positive");
-  if (L > kMaxL) return fail(OM_EINVAL, "om_encode: L=%d exceeds the supported maximum of %d tokens", L, kMaxL);
+  const bool long_seq = L > kMaxL;
+  if (long_seq && (L > kMaxLongL || L % 128 != 0))
+    return fail(OM_EINVAL, "om_encode: L=%d unsupported (at most %d tokens, or 256 / 384 / 512: pad to a multiple of 128)", L,
+                kMaxL);
   const om_encoder_desc& d = e->d;
   if (d.arch == OM_ARCH_BERT && L > d.max_pos) return fail(OM_EINVAL, "om_encode: L=%d exceeds max_position_embeddings", L);
   const int64_t T64 = static_cast<int64_t>(B) * L;
@@ -1013,18 +1207,18 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
   OM_CUDA(cudaGetLastError());
 
   // attention geometry
-  const int spt = L > 64 ? 1 : kMaxL / L;
+  const int spt = L > 64 ? 1 : kMaxL / L;  // sequences per 128-row tile (long sequences: L / 128 tiles per sequence)
   AttnParams ap;
   ap.T = T;
   ap.L = L;
   ap.spt = spt;
   ap.I = I;
-  ap.Tvalid_rows = spt * L;
+  ap.Tvalid_rows = long_seq ? 128 : spt * L;
   ap.scale_log2 = (bert ? 0.125f : 1.0f) * kLog2e;
   ap.kmask = e->kmask;
-  ap.relbias_log2 = bert ? nullptr : e->relbias_log2;
+  ap.relbias_log2 = bert ? nullptr : (long_seq ? e->relbias_long_log2 : e->relbias_log2);
   ap.ctx = e->ctx;
-  const int n_tiles = (B + spt - 1) / spt;
+  const int n_tiles = long_seq ? T / 128 : (B + spt - 1) / spt;
   CUtensorMap tmQK, tmVt;
   if (make_tmap_bf16_2d(&tmQK, e->qk, (uint64_t)2 * I, (uint64_t)T, (uint64_t)2 * I * 2, 64, 128) != 0 ||
       make_tmap_bf16_2d(&tmVt, e->vt, (uint64_t)n_tiles * 128, (uint64_t)I, (uint64_t)e->Tld * 2, 64, 64) != 0)
@@ -1045,11 +1239,14 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       pending = nullptr;
     }
     {
-      EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, spt * L};
+      EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, ap.Tvalid_rows};
       cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
     }
-    attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
+    if (long_seq)
+      attn_long_kernel<<<dim3(n_tiles, d.heads), 128, kAttnLongSmemBytes, st>>>(tmQK, tmVt, ap);
+    else
+      attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
     OM_CUDA(cudaGetLastError());
     {
       // N = H: 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2

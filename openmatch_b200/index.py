@@ -30,6 +30,7 @@ class FlatIPIndex:
         _lib.check(self._lib.om_index_create(int(d), ctypes.byref(h)))
         self._h = h
         self.d = int(d)
+        self._pending = None  # (nq, k, device) between search_begin and search_finish
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -99,10 +100,15 @@ class FlatIPIndex:
         self._pending = (q.shape[0], int(k), q.device)
         return rng
 
+    def _require_pending(self, what: str):
+        if self._pending is None:
+            raise RuntimeError("%s: no search in progress (call search_begin first)" % what)
+        return self._pending
+
     def search_count(self, global_range: torch.Tensor) -> torch.Tensor:
         """Phase 2: histogram (CUDA int32 [nq, bins]) of the local candidates over the reduced score range, to be
         SUM-reduced over the shards."""
-        nq, _, dev = self._pending
+        nq, _, dev = self._require_pending("search_count")
         hist = torch.empty((nq, self._lib.om_search_floor_bins()), dtype=torch.int32, device=dev)
         _lib.check(self._lib.om_index_search_count(self._h, global_range.data_ptr(), hist.data_ptr(), _stream()))
         return hist
@@ -111,7 +117,8 @@ class FlatIPIndex:
                       id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Phase 3: fp32 re-score of the local candidates at or above the agreed floor -> (D [nq, k], I [nq, k],
         kept [1] int32 = longest valid prefix over the queries), all on the device."""
-        nq, k, dev = self._pending
+        nq, k, dev = self._require_pending("search_finish")
+        self._pending = None
         D = torch.empty((nq, k), dtype=torch.float32, device=dev)
         I = torch.empty((nq, k), dtype=torch.int64, device=dev)
         kept = torch.empty((1,), dtype=torch.int32, device=dev)

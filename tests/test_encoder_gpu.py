@@ -192,6 +192,46 @@ def test_t5_base_vs_oracle(enc_mod, L, B):
     _check(reps.cpu().numpy(), oreps.numpy(), "reps")
 
 
+@pytest.mark.parametrize("L,B", [(256, 3), (384, 2), (512, 2)])
+def test_bert_long_sequences_vs_oracle(enc_mod, L, B):
+    # sequences longer than one attention tile: online softmax over 128-key tiles (attn_long_kernel)
+    gen = torch.Generator().manual_seed(300 + L)
+    layers, H, F, vocab = 2, 768, 3072, 2000
+    sd = _rand_bert_sd(gen, layers, H, F, vocab, 512)
+    spec = dict(arch="bert", layers=layers, hidden=H, heads=12, ffn=F, vocab=vocab, max_pos=512, type_vocab=2,
+                ln_eps=1e-12)
+    enc = enc_mod.CudaEncoder(spec, sd, pooling="first", max_batch_tokens=B * L)
+    ids, mask = _ids(gen, B, L, vocab)
+    mask[1, 5:] = 0  # whole key tiles masked out: the running max must survive tiles without any allowed key
+    ids[1, 5:] = 0
+    tt = torch.randint(0, 2, (B, L), generator=gen)
+    hidden, reps = enc.encode(ids.cuda(), mask.cuda(), tt.cuda(), return_hidden=True)
+    ospec = EncoderSpec("bert", layers, H, 12, F, 1e-12, pooling="first")
+    oh, oreps = oracle.encode_reps(sd, ospec, ids, mask, tt)
+    m = mask.numpy().astype(bool)
+    _check(reps.cpu().numpy(), oreps.numpy(), "reps")
+    _check(hidden.cpu().numpy()[m], oh.numpy()[m], "hidden")
+
+
+@pytest.mark.parametrize("L,B", [(256, 2), (512, 1)])
+def test_t5_long_sequences_vs_oracle(enc_mod, L, B):
+    # relative-position bias beyond +-127 (bucket saturation at max_distance) through the 1023-entry table
+    gen = torch.Generator().manual_seed(400 + L)
+    layers, H, heads, F, vocab = 2, 768, 12, 3072, 2000
+    sd = _rand_t5_sd(gen, layers, H, heads, F, vocab)
+    head_w = torch.randn(768, 768, generator=gen) * 768 ** -0.5
+    spec = dict(arch="t5", layers=layers, hidden=H, heads=heads, ffn=F, vocab=vocab, ln_eps=1e-6, rel_buckets=32,
+                rel_max_distance=128)
+    enc = enc_mod.CudaEncoder(spec, sd, head_weight=head_w, pooling="mean", normalize=True, max_batch_tokens=B * L)
+    ids, mask = _ids(gen, B, L, vocab)
+    hidden, reps = enc.encode(ids.cuda(), mask.cuda(), return_hidden=True)
+    ospec = EncoderSpec("t5", layers, H, heads, F, 1e-6, pooling="mean", normalize=True)
+    oh, oreps = oracle.encode_reps(sd, ospec, ids, mask, head_weight=head_w)
+    m = mask.numpy().astype(bool)
+    _check(hidden.cpu().numpy()[m], oh.numpy()[m], "hidden")
+    _check(reps.cpu().numpy(), oreps.numpy(), "reps")
+
+
 def test_encoder_errors(enc_mod):
     gen = torch.Generator().manual_seed(1)
     sd = _rand_bert_sd(gen, 1, 128, 256, 100, 64)
@@ -201,7 +241,7 @@ def test_encoder_errors(enc_mod):
     with pytest.raises(RuntimeError):
         enc.encode(ids, mask)  # CPU tensors: no CPU path
     with pytest.raises(RuntimeError):
-        enc.encode(torch.zeros(3, 129, dtype=torch.long).cuda(), torch.ones(3, 129, dtype=torch.long).cuda())
+        enc.encode(torch.zeros(1, 130, dtype=torch.long).cuda(), torch.ones(1, 130, dtype=torch.long).cuda())  # 128 < L, L % 128 != 0
     with pytest.raises(RuntimeError):
         enc.encode(torch.zeros(64, 16, dtype=torch.long).cuda(), torch.ones(64, 16, dtype=torch.long).cuda())
     del sd["encoder.layer.0.output.dense.bias"]
