@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from openmatch_b200.index import FlatIPIndex
 
 torch.manual_seed(0)
-d = 768
+d = int(os.environ.get("OM_D", 768))
 cases = [(1_000_000, 6980, 1000), (1_000_000, 128, 1000), (8_800_000, 6980, 1000), (8_800_000, 6980, 100)]
 if len(sys.argv) > 1:
     cases = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
