@@ -3,13 +3,17 @@
 //   run  : build/selftest_gemm [dump_dir]
 // Exact check: small-integer bf16 operands make every product and partial sum exactly representable
 // in fp32, so the tensor-core result must equal the CPU result bit for bit.
+#include <execinfo.h>
 #include <math.h>
+#include <signal.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 #include "gemm.cuh"
+#include "gemm2sm.cuh"
 #include "scan_epilogue.cuh"
 
 using namespace om;
@@ -124,6 +128,133 @@ static int check_case(int M, int N, int K, int num_sms, const char* dump_dir, bo
 }
 
 template <int BN, int STAGES, bool MF, int EW = 4>
+static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters);
+
+// 2-CTA (cta_group::2) core: same exact check
+template <int STAGES, bool MF, int EW>
+static int check_case2(int M, int N, int K, int num_sms) {
+  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, M, N, K);
+  fflush(stdout);
+  std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
+  std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
+  for (size_t i = 0; i < hA.size(); ++i) {
+    fA[i] = (float)((int)(rnd() % 7) - 3);
+    hA[i] = __float2bfloat16(fA[i]);
+  }
+  for (size_t i = 0; i < hB.size(); ++i) {
+    fB[i] = (float)((int)(rnd() % 7) - 3);
+    hB[i] = __float2bfloat16(fB[i]);
+  }
+  __nv_bfloat16 *dA, *dB;
+  float* dC;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dC, (size_t)M * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
+  EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
+  printf("[launch] "); fflush(stdout);
+  cudaError_t e = launch_gemm2<STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  printf("[launched %d] ", (int)e); fflush(stdout);
+  if (e != cudaSuccess) {
+    printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("KERNEL FAILED: %s\n", cudaGetErrorString(e));
+    exit(3);
+  }
+  printf("[synced] "); fflush(stdout);
+  unsigned int fault = read_clear_dev_fault();
+  printf("[fault %x] ", fault); fflush(stdout);
+  if (fault) printf("DEVICE FAULT word=0x%08x (site %u, block %u) ", fault, (fault >> 16) & 0x7fff, fault & 0xffff);
+  std::vector<float> hC((size_t)M * N);
+  CK(cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost));
+  printf("[copied] "); fflush(stdout);
+  size_t bad = 0;
+  int printed = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float ref = 0;
+      for (int k = 0; k < K; ++k) ref += fA[(size_t)m * K + k] * fB[(size_t)n * K + k];
+      const float got = hC[(size_t)m * N + n];
+      if (!(got == ref)) {
+        ++bad;
+        if (printed < 8) {
+          printf("\n   mismatch C[%d,%d] got %g want %g", m, n, got, ref);
+          ++printed;
+        }
+      }
+    }
+  printf("%s  (%zu / %zu mismatches)\n", bad ? "\n   FAIL" : "ok", bad, hC.size());
+  cudaFree(dA), cudaFree(dB), cudaFree(dC);
+  return (bad || fault) ? 1 : 0;
+}
+
+template <int STAGES, bool MF, int EW, int SPIN = 0>
+static void perf_case2(const char* name, int M, int N, int K, int num_sms, int iters) {
+  __nv_bfloat16 *dA, *dB;
+  unsigned long long* dcnt;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dcnt, 8));
+  CK(cudaMemset(dcnt, 0, 8));
+  {
+    std::vector<uint16_t> h((size_t)1 << 22);
+    for (auto& x : h) x = (uint16_t)(0x3c00 + (rnd() % 0x400)) | (uint16_t)((rnd() & 1) << 15);
+    for (size_t off = 0; off < (size_t)M * K; off += h.size())
+      CK(cudaMemcpy(dA + off, h.data(), std::min(h.size(), (size_t)M * K - off) * 2, cudaMemcpyHostToDevice));
+    for (size_t off = 0; off < (size_t)N * K; off += h.size())
+      CK(cudaMemcpy(dB + off, h.data(), std::min(h.size(), (size_t)N * K - off) * 2, cudaMemcpyHostToDevice));
+  }
+  EpiCount epi{dcnt, 1.0e30f, M, N};
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int pairs = 0;
+  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= iters;
+  unsigned int fault = read_clear_dev_fault();
+  double tf = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
+  printf("[perf 2sm spin=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", SPIN, name, STAGES,
+         (int)MF, EW, pairs, M, N, K, ms, tf, fault);
+  fflush(stdout);
+  cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
+}
+
+static int run_2sm(int sms) {
+  int fails = 0;
+  fails += check_case2<6, false, 4>(256, 256, 64, sms);     // one pair tile, one k-block
+  if (fails) return fails;                                  // nothing else can work
+  fails += check_case2<6, false, 8>(300, 520, 192, sms);    // ragged edges, several tiles
+  // one variable at a time: wait flavour (suspending try_wait vs spinning test_wait) x ring depth
+  perf_case2<6, false, 8, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 1>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<3, false, 8, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<3, false, 8, 1>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case<256, 4, false, 8>("encoder FFN1 shape (1-CTA)", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 1>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8, 0>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
+  perf_case<256, 4, false, 8>("cublas-peak shape 8192^3 (1-CTA)", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, true, 8, 1>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12);
+  perf_case<256, 4, true, 8>("search 6980 x 4M sustained (1-CTA)", 6980, 1 << 22, 768, sms, 12);
+  fflush(stdout);
+  fails += check_case2<6, false, 4>(256, 256, 512, sms);    // ring wraps
+  fails += check_case2<6, true, 8>(1000, 3000, 768, sms);   // both accumulator buffers, M fastest
+  fails += check_case2<6, false, 8>(2048, 2304, 768, sms);  // many tiles per pair
+  return fails;
+}
+
+template <int BN, int STAGES, bool MF, int EW>
 static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters) {
   __nv_bfloat16 *dA, *dB;
   unsigned long long* dcnt;
@@ -218,7 +349,19 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   cudaFree(dA), cudaFree(dB), cudaFree(thr), cudaFree(cand), cudaFree(count), cudaFree(ovf);
 }
 
+static void on_segv(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "\n*** fatal signal, backtrace:\n";
+  (void)!write(1, msg, sizeof msg - 1);
+  backtrace_symbols_fd(frames, n, 1);
+  _exit(128 + sig);
+}
+
 int main(int argc, char** argv) {
+  signal(SIGSEGV, on_segv);
+  signal(SIGABRT, on_segv);
+  signal(SIGBUS, on_segv);
   const char* dump_dir = argc > 1 ? argv[1] : nullptr;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -226,6 +369,11 @@ int main(int argc, char** argv) {
          prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
   const int sms = prop.multiProcessorCount;
   int fails = 0;
+  if (argc > 1 && strcmp(argv[1], "--2sm") == 0) {
+    const int f2 = run_2sm(sms);
+    printf("2sm: %d failing case(s)\n", f2);
+    return f2 ? 1 : 0;
+  }
   fails += check_case<256, 4, false>(128, 256, 64, sms, dump_dir);   // one tile, one k-block
   fails += check_case<256, 4, false>(128, 256, 256, sms, dump_dir);  // one tile, ring wraps once
   fails += check_case<256, 4, false>(300, 520, 192, sms, dump_dir);  // ragged edges, several tiles
