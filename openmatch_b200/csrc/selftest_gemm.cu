@@ -154,9 +154,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
-  printf("[launch] "); fflush(stdout);
   cudaError_t e = launch_gemm2<STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
-  printf("[launched %d] ", (int)e); fflush(stdout);
   if (e != cudaSuccess) {
     printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
     return 1;
@@ -166,13 +164,10 @@ static int check_case2(int M, int N, int K, int num_sms) {
     printf("KERNEL FAILED: %s\n", cudaGetErrorString(e));
     exit(3);
   }
-  printf("[synced] "); fflush(stdout);
   unsigned int fault = read_clear_dev_fault();
-  printf("[fault %x] ", fault); fflush(stdout);
   if (fault) printf("DEVICE FAULT word=0x%08x (site %u, block %u) ", fault, (fault >> 16) & 0x7fff, fault & 0xffff);
   std::vector<float> hC((size_t)M * N);
   CK(cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost));
-  printf("[copied] "); fflush(stdout);
   size_t bad = 0;
   int printed = 0;
   for (int m = 0; m < M; ++m)
