@@ -1,6 +1,5 @@
 """Scratch probe (not part of the product): encoder throughput on the GPU, synthetic bert-base / t5-base."""
 import sys
-import time
 
 import torch
 
