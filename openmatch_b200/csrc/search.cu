@@ -30,6 +30,10 @@
 #include "gemm.cuh"
 #include "scan_epilogue.cuh"
 
+#ifndef OM_SCAN_VARIANT
+#define OM_SCAN_VARIANT 0  // filter code shape, see scan_epilogue.cuh (1 / 2: unmeasured candidates)
+#endif
+
 namespace om {
 
 // ---------------------------------------------------------------------------------------------------
@@ -665,7 +669,8 @@ int sweep(om_index* ix, const __nv_bfloat16* qb, int nq, int kp, int C, int grow
         e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st,
                                          ix->dynamic_sched != 0);
       } else {
-        EpiScan<false> epi{w.thr, w.cand, w.count, w.overflow, nq, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
+        EpiScan<false, 256, OM_SCAN_VARIANT> epi{w.thr, w.cand, w.count, w.overflow, nq, static_cast<int>(step), C,
+                                                 static_cast<uint32_t>(pos)};
         e = launch_gemm<256, 4, true, 8>(qb, ix->dpad, xrows, ix->dpad, nq, static_cast<int>(step), ix->d, epi, sms, st,
                                          ix->dynamic_sched != 0);
       }
