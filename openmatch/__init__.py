@@ -13,5 +13,5 @@ for _name in ("arguments", "utils", "loss", "modeling", "dataset", "trainer", "r
     globals()[_name] = _mod
 for _sub in ("modeling.dense_retrieval_model", "modeling.linear", "retriever.dense_retriever", "trainer.dense_trainer",
              "dataset.data_collator", "dataset.inference_dataset", "dataset.train_dataset", "driver.build_index",
-             "driver.retrieve", "driver.train_dr"):
+             "driver.retrieve", "driver.successive_retrieve", "driver.train_dr"):
     sys.modules[__name__ + "." + _sub] = importlib.import_module("openmatch_b200." + _sub)

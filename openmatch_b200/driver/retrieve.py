@@ -7,7 +7,6 @@ from ..arguments import DataArguments, InferenceArguments as EncodingArguments, 
 from ..dataset import InferenceDataset
 from ..modeling import DRModelForInference
 from ..retriever import Retriever
-from ..utils import save_as_trec
 from ._common import load_config, load_tokenizer, parse, setup_logging
 
 logger = logging.getLogger(__name__)
@@ -26,9 +25,11 @@ def main():
                                           num_processes=encoding_args.world_size,
                                           process_index=encoding_args.process_index, cache_dir=model_args.cache_dir)
     retriever = Retriever.from_embeddings(model, encoding_args)
-    result = retriever.retrieve(query_dataset, topk=encoding_args.retrieve_depth)
+    # ranked arrays -> TREC lines directly (same bytes as save_as_trec on the reference's dict, minus the
+    # 7 M-entry dict-of-dicts of a top-1000 MS MARCO run)
+    result = retriever.retrieve(query_dataset, topk=encoding_args.retrieve_depth, as_arrays=True)
     if encoding_args.process_index == 0:
-        save_as_trec(result, encoding_args.trec_save_path)
+        result.save_trec(encoding_args.trec_save_path)
 
 
 if __name__ == '__main__':

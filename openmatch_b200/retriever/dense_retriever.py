@@ -49,6 +49,30 @@ def _results_dict(query_ids: List[str], doc_lookup: np.ndarray, D: np.ndarray, I
     return out
 
 
+class RankArrays:
+    """Search output kept as arrays (``Retriever.search(..., as_arrays=True)``): row ``i`` of ``I`` / ``D`` holds the
+    ranked rows of ``doc_names`` / scores for ``query_ids[i]``; ``to_dict()`` gives the reference's dict-of-dicts."""
+
+    def __init__(self, query_ids, doc_names, D, I):
+        self.query_ids, self.doc_names, self.D, self.I = list(query_ids), np.asarray(doc_names), D, I
+
+    def to_dict(self) -> Dict[str, Dict[str, float]]:
+        return _results_dict(self.query_ids, self.doc_names, self.D, self.I)
+
+    def unique_doc_ids(self) -> bool:
+        return len(set(self.doc_names.tolist())) == self.doc_names.shape[0]
+
+    def save_trec(self, path: str, run_id: str = "OpenMatch"):
+        from ..utils import save_as_trec, save_trec_arrays
+        if self.unique_doc_ids():
+            save_trec_arrays(self.query_ids, self.doc_names, self.I, self.D, path, run_id)
+        else:  # duplicated doc-id strings collapse in the reference's dict (dense_retriever.py:186-187)
+            save_as_trec(self.to_dict(), path, run_id)
+
+    def __len__(self):
+        return len(self.query_ids)
+
+
 class Retriever:
 
     def __init__(self, model: DRModelForInference, corpus_dataset: IterableDataset, args: EncodingArguments):
@@ -185,19 +209,21 @@ class Retriever:
             self.query_lookup.extend(lookup)
         return np.concatenate(encoded)
 
-    def search(self, topk: int = 100):
+    def search(self, topk: int = 100, as_arrays: bool = False):
+        """Reference contract (:166-192): ``{qid: {docid: score}}``.  ``as_arrays=True`` returns the same ranking as
+        a :class:`RankArrays` (no per-result Python objects; rank 0 only when sharded)."""
         logger.info("Searching")
         if self.index is None:
             raise ValueError("Index is not initialized")
         encoded = self._load_queries()
         if self.args.world_size > 1:
-            return self._search_sharded(encoded, topk)
+            return self._search_sharded(encoded, topk, as_arrays)
         D, I = self.index.search(encoded, topk)
-        result = _results_dict(self.query_lookup, np.array(self.doc_lookup), D, I)
+        result = RankArrays(self.query_lookup, np.array(self.doc_lookup), D, I)
         logger.info("End searching with %d queries", len(result))
-        return result
+        return result if as_arrays else result.to_dict()
 
-    def _search_sharded(self, encoded: np.ndarray, topk: int):
+    def _search_sharded(self, encoded: np.ndarray, topk: int, as_arrays: bool = False):
         """Every rank: all queries x local shard -> all-gather [nq, k] lists over NCCL -> merge; doc-id strings
         are gathered to rank 0, which alone builds the result dict (like the reference, :200-203)."""
         dist = torch.distributed
@@ -210,20 +236,21 @@ class Retriever:
         lookups = [None] * W if r == 0 else None
         dist.gather_object(self.doc_lookup, lookups, dst=0)
         if r != 0:
-            return {}
+            return RankArrays([], [], None, None) if as_arrays else {}
         names = np.array([d for part in lookups for d in part])
-        return _results_dict(self.query_lookup, names, D.cpu().numpy(), I.cpu().numpy())
+        result = RankArrays(self.query_lookup, names, D.cpu().numpy(), I.cpu().numpy())
+        return result if as_arrays else result.to_dict()
 
-    def retrieve(self, query_dataset: IterableDataset, topk: int = 100):
+    def retrieve(self, query_dataset: IterableDataset, topk: int = 100, as_arrays: bool = False):
         self.query_embedding_inference(query_dataset)
         self.model.cpu()
         del self.model
         torch.cuda.empty_cache()
         if self.args.world_size > 1:
-            results = self.search(topk)  # collective: every rank takes part, rank 0 gets the dict
+            results = self.search(topk, as_arrays)  # collective: every rank takes part, rank 0 gets the result
             torch.distributed.barrier()
             return results
-        return self.search(topk)
+        return self.search(topk, as_arrays)
 
 
 class SuccessiveRetriever(Retriever):

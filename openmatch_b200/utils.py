@@ -35,6 +35,27 @@ def save_as_trec(rank_result: Dict[str, Dict[str, float]], output_path: str, run
             out.writelines("{} Q0 {} {} {} {}\n".format(qid, did, r + 1, s, run_id) for r, (did, s) in enumerate(ranked))
 
 
+def save_trec_arrays(query_ids, doc_names, I, D, output_path: str, run_id: str = "OpenMatch"):
+    """Array form of :func:`save_as_trec` for search output that is still in (I, D) form: ``I`` int64 [nq, k] rows
+    into ``doc_names`` (-1 = padding), ``D`` float32 [nq, k] sorted descending per row.  Writes byte-for-byte what
+    ``save_as_trec`` writes for the equivalent ``{qid: {docid: score}}`` dict (scores print as ``float(np.float32)``,
+    utils.py:126-136 / dense_retriever.py:183-188) without building the 7 M-entry dict of a top-1000 MS MARCO run.
+    Precondition (checked by the caller): doc ids are unique, so the dict would not have merged any entries."""
+    import numpy as np
+    names = np.asarray(doc_names)
+    I = np.asarray(I)
+    scores = np.asarray(D, dtype=np.float64)
+    with open(output_path, "w") as out:
+        for qi, qid in enumerate(query_ids):
+            row = I[qi]
+            n = int((row >= 0).sum()) if (row < 0).any() else row.shape[0]  # padding is a suffix
+            docs = names[row[:n]].tolist()
+            vals = scores[qi, :n].tolist()
+            qid = str(qid)
+            out.write("".join("{} Q0 {} {} {} {}\n".format(qid, d, r + 1, v, run_id)
+                              for r, (d, v) in enumerate(zip(docs, vals))))
+
+
 def load_from_trec(input_path: str, as_list: bool = False, max_len_per_q: int = None):
     """Reads 6-column TREC runs or 3-column ``qid docid score`` files (utils.py:139-169)."""
     result, seen = {}, 0

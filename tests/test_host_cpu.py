@@ -17,9 +17,9 @@ def test_drop_in_alias_modules():
     from openmatch.loss import DistributedContrastiveLoss, SimpleContrastiveLoss  # noqa: F401
     from openmatch.modeling import DRModel, DRModelForInference, DROutput, LinearHead  # noqa: F401
     from openmatch.retriever import FaissRetriever, Retriever, SuccessiveRetriever
-    from openmatch.driver import build_index, retrieve, train_dr
+    from openmatch.driver import build_index, retrieve, successive_retrieve, train_dr
     assert FaissRetriever is Retriever and issubclass(SuccessiveRetriever, Retriever)
-    for mod in (build_index, retrieve, train_dr):
+    for mod in (build_index, retrieve, successive_retrieve, train_dr):
         assert callable(mod.main)
     assert openmatch.modeling.DRModel is DRModel
 
@@ -163,3 +163,38 @@ def test_model_refuses_cpu_tensors():
     m = DRModelForInference(lm_q=Dummy(), lm_p=Dummy())
     with pytest.raises(RuntimeError, match="no CPU path"):
         m.encode_passage({"input_ids": torch.zeros(1, 4, dtype=torch.long), "attention_mask": torch.ones(1, 4, dtype=torch.long)})
+
+
+def test_rank_arrays_and_vectorised_trec_writer_match_the_dict_path(tmp_path):
+    # Retriever.search(as_arrays=True) + RankArrays.save_trec must write byte-for-byte what the reference's
+    # dict-of-dicts + save_as_trec writes (dense_retriever.py:183-188, utils.py:126-136), padding included
+    import types
+
+    import oracle
+    from openmatch_b200.retriever.dense_retriever import RankArrays, Retriever, _results_dict
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((40, 16)).astype(np.float32)
+    q = rng.standard_normal((7, 16)).astype(np.float32)
+    idx = oracle.FlatIPIndex(16)
+    idx.add(x)
+    r = Retriever.__new__(Retriever)
+    r.index = idx
+    r.args = types.SimpleNamespace(world_size=1)
+    r.doc_lookup = ["doc%03d" % i for i in range(40)]
+    r.query_lookup = ["q%d" % i for i in range(7)]
+    r._load_queries = lambda: q
+    for topk in (5, 40, 64):  # 64 > ntotal: -1 padded tail
+        as_dict = r.search(topk)
+        arrays = r.search(topk, as_arrays=True)
+        assert isinstance(arrays, RankArrays) and arrays.to_dict() == as_dict
+        assert all(len(v) == min(topk, 40) for v in as_dict.values())
+        a, b = tmp_path / ("dict.%d.trec" % topk), tmp_path / ("arr.%d.trec" % topk)
+        utils.save_as_trec(as_dict, str(a))
+        arrays.save_trec(str(b))
+        assert a.read_bytes() == b.read_bytes()
+    # duplicated doc-id strings: the dict merges them, so the writer must fall back to the dict path
+    dup = RankArrays(["q0"], np.array(["a", "b", "a"]), np.array([[3.0, 2.0, 1.0]], np.float32), np.array([[0, 1, 2]]))
+    assert not dup.unique_doc_ids()
+    dup.save_trec(str(tmp_path / "dup.trec"))
+    utils.save_as_trec(_results_dict(["q0"], np.array(["a", "b", "a"]), dup.D, dup.I), str(tmp_path / "dup2.trec"))
+    assert (tmp_path / "dup.trec").read_bytes() == (tmp_path / "dup2.trec").read_bytes()
