@@ -48,6 +48,10 @@ __host__ __device__ __forceinline__ float key_score(unsigned long long k) {
 //   1  candidate for the next round (unmeasured): 4 group maxima of 8 columns; only groups that beat the
 //      threshold are expanded (8-bit mask, 7-SEL tree), the group's 8 values chosen by a select on the group id
 //   2  candidate (unmeasured): like 1 with the four group bodies unrolled (no group select, more cold code)
+//   3  candidate (unmeasured): warp-cooperative extraction - a lane whose chunk beats its threshold broadcasts its
+//      32 values with 32 shuffles so that lane i holds column i; one compare + ballot finds every survivor of the
+//      chunk at once and the surviving lanes store their own keys (no mask loop, no select tree, no single-lane
+//      dependent chain; cost independent of the number of survivors in the chunk)
 // Measured with selftest perf_scan (variant 0): 1 survivor per warp-tile costs ~15 % of the scan rate, i.e. about
 // a thousand cycles of a single-lane dependent chain per survivor - the term to shrink.
 template <bool DENSE, int EPI_THREADS = 256, int VARIANT = 0>
@@ -130,6 +134,10 @@ struct EpiScan {
     }
   }
   __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int pass) const {
+    if constexpr (VARIANT == 3 && !DENSE) {
+      chunk_coop(s, row, col0, v, pass);  // warp-collective: every lane stays in
+      return;
+    }
     if (row >= nq || col0 >= n_cols) return;
     unsigned long long* mine = cand + static_cast<size_t>(row) * C;
     if constexpr (DENSE) {
@@ -259,6 +267,58 @@ struct EpiScan {
           w[j] = (q & 2) ? hi : lo;
         }
         expand_group(s, w, col0 + 8 * q, lim - 8 * q, t, pass, mine);
+      }
+    }
+  }
+  // VARIANT 3 (see the struct comment).  Must be called by all 32 lanes of the warp (the GEMM epilogue loop is
+  // warp-uniform).  Survivors are appended in increasing column order, exactly like variant 0.
+  __device__ __forceinline__ void chunk_coop(State& s, int row, int col0, const float (&v)[32], int pass) const {
+    const unsigned full = 0xffffffffu;
+    const int lane = static_cast<int>(threadIdx.x & 31u);
+    if (col0 >= n_cols) return;  // warp-uniform
+    const bool active = row < nq && !(pass == 1 && s.n <= kStash);
+    float mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+    unsigned hot = __ballot_sync(full, active && mx > s.t);
+    if (hot == 0u) return;  // common case: no lane of the warp has a survivor in this chunk
+    const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
+#pragma unroll 1
+    while (hot) {
+      const int L = __ffs(hot) - 1;  // the lane (query row) being expanded
+      hot &= hot - 1;
+      float x = 0.f;  // lane i receives column i of lane L's chunk
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float y = __shfl_sync(full, v[i], L);
+        if (lane == i) x = y;
+      }
+      const float tL = __shfl_sync(full, s.t, L);
+      const int rowL = __shfl_sync(full, row, L);
+      const bool sv = x > tL && lane < lim;
+      const unsigned m = __ballot_sync(full, sv);
+      const int cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+      const unsigned long long key = make_key(x, row_base + col0 + lane);
+      if (pass == 0) {
+        const int kL = __shfl_sync(full, s.k, L), bufL = __shfl_sync(full, s.buf, L);
+        const int j = kL + rank;
+        if (sv && j < kStash)
+          s.stash[(static_cast<size_t>(bufL) * kStash + j) * kEpiThreads + (s.tid - lane + L)] = key;
+        if (lane == L) {
+          s.k = kL + cnt < kStash ? kL + cnt : kStash;
+          s.n += cnt;
+        }
+      } else {
+        const int skipL = __shfl_sync(full, s.skip, L), posL = __shfl_sync(full, s.pos2, L);
+        if (sv && rank >= skipL) {
+          const int p = posL + (rank - skipL);
+          if (p < C) cand[static_cast<size_t>(rowL) * C + p] = key;
+        }
+        if (lane == L) {
+          const int used = cnt < skipL ? cnt : skipL;
+          s.skip = skipL - used;
+          s.pos2 = posL + (cnt - used);
+        }
       }
     }
   }

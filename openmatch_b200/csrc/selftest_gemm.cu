@@ -374,16 +374,27 @@ static void on_segv(int sig) {
 // filter variants of scan_epilogue.cuh: same survivor sets (exact), cost per survivor compared at several rates
 static int run_scan_variants(int sms) {
   int fails = 0;
-  std::vector<unsigned long long> k0, k1, k2;
+  std::vector<unsigned long long> k0, k1, k2, k3;
   perf_scan<8, 0>("variant check", 1000, 1 << 16, 768, sms, 1, 36.f, true, &k0);
   perf_scan<8, 1>("variant check", 1000, 1 << 16, 768, sms, 1, 36.f, true, &k1);
   perf_scan<8, 2>("variant check", 1000, 1 << 16, 768, sms, 1, 36.f, true, &k2);
-  printf("[scanvar] survivor sets: v1 %s v0, v2 %s v0 (%zu keys)\n", k1 == k0 ? "==" : "!=", k2 == k0 ? "==" : "!=", k0.size());
-  fails += (k1 != k0) + (k2 != k0) + (k0.size() < 2000);
+  perf_scan<8, 3>("variant check", 1000, 1 << 16, 768, sms, 1, 36.f, true, &k3);
+  printf("[scanvar] survivor sets: v1 %s v0, v2 %s v0, v3 %s v0 (%zu keys)\n", k1 == k0 ? "==" : "!=",
+         k2 == k0 ? "==" : "!=", k3 == k0 ? "==" : "!=", k0.size());
+  fails += (k1 != k0) + (k2 != k0) + (k3 != k0) + (k0.size() < 2000);
+  // dense-ish threshold: > kStash survivors per (thread, tile) exercises the second pass of every variant
+  perf_scan<8, 0>("variant check, overflow pass", 300, 1 << 14, 768, sms, 1, 20.f, true, &k0);
+  perf_scan<8, 1>("variant check, overflow pass", 300, 1 << 14, 768, sms, 1, 20.f, true, &k1);
+  perf_scan<8, 2>("variant check, overflow pass", 300, 1 << 14, 768, sms, 1, 20.f, true, &k2);
+  perf_scan<8, 3>("variant check, overflow pass", 300, 1 << 14, 768, sms, 1, 20.f, true, &k3);
+  printf("[scanvar] overflow pass: v1 %s v0, v2 %s v0, v3 %s v0 (%zu keys)\n", k1 == k0 ? "==" : "!=",
+         k2 == k0 ? "==" : "!=", k3 == k0 ? "==" : "!=", k0.size());
+  fails += (k1 != k0) + (k2 != k0) + (k3 != k0);
   for (float t : {1e30f, 42.f, 38.f, 35.f, 32.f}) {
     perf_scan<8, 0>("scan 1M", 6980, 1 << 20, 768, sms, 3, t, true);
     perf_scan<8, 1>("scan 1M", 6980, 1 << 20, 768, sms, 3, t, true);
     perf_scan<8, 2>("scan 1M", 6980, 1 << 20, 768, sms, 3, t, true);
+    perf_scan<8, 3>("scan 1M", 6980, 1 << 20, 768, sms, 3, t, true);
   }
   return fails;
 }
