@@ -233,6 +233,28 @@ def main():
     e2e_ms = timed(e2e_step, args.steps, min(args.warmup, 2)) / args.steps
     e2e_qps = nq / (e2e_ms * 1e-3)
 
+    # ---------------- streaming regime: few queries per pass -> one sweep of the bf16 shard is
+    # HBM-bound.  Local shard only (no exchange), k = 100; roofline = rows_local * d * 2 B per sweep / measured HBM
+    streaming = None
+    if not args.skip_encode:
+        try:
+            streaming = {"unit": "ms per search over this GPU's shard", "k": 100, "cases": {}}
+            hbm = measured_peaks().get("hbm")
+            sweep_bytes = (hi - lo) * d * 2.0
+            for snq in (1, 16, 64):
+                qs = q_dev[:snq].contiguous()
+
+                def stream_step():
+                    idx.search_device(qs, 100)
+
+                sms_ = timed(stream_step, 10, 3) / 10
+                case = {"ms": sms_, "queries_per_s": world * snq / (sms_ * 1e-3), "achieved_gbs": sweep_bytes / (sms_ * 1e-3) / 1e9}
+                if hbm:
+                    case["frac_of_hbm_peak"] = case["achieved_gbs"] / hbm
+                streaming["cases"]["nq=%d" % snq] = case
+        except Exception as e:  # informational leg
+            streaming = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---------------- encoder throughput (bert-base, L=128, one batch per step per GPU) ----------------
     encode = None
     if not args.skip_encode:
@@ -393,6 +415,8 @@ def main():
         line["loss"] = loss_obj
     if train_obj:
         line["train"] = train_obj
+    if streaming:
+        line["streaming"] = streaming
     if world == 1 and not args.skip_cpu:
         base = cpu_reference_search(args, 1, 0)
         line["cpu_baseline"] = {k_: base[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
