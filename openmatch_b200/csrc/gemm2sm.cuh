@@ -89,6 +89,19 @@ __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t d_tmem, uint64_t a_des
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the 9-operand form CUTLASS emits (explicit all-zero disable-output-lane mask)
+__device__ __forceinline__ void umma_bf16_ss_2sm_masked(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                        uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
 // arrive (count 1) on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so
 // far have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
@@ -152,23 +165,25 @@ __device__ __forceinline__ void wait2_warp(uint64_t* bar, uint32_t parity, uint3
   }
 }
 
-template <int STAGES>
+template <int STAGES, int TILE_N = 256>
 struct Gemm2Cfg {
-  static constexpr int kTileM = 256, kTileN = 256;          // per CTA pair
+  static_assert(TILE_N == 256 || TILE_N == 128, "pair tile N: 256 or 128");
+  static constexpr int kTileM = 256, kTileN = TILE_N;       // per CTA pair
   static constexpr int kABytes = kBlockM * kBlockK * 2;       // this CTA's 128 A rows
   static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;  // this CTA's half of B
   static constexpr int kStageBytes = kABytes + kBBytes;       // 32 KB
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kEpiOffset = kBarOffset + 1024;
   static constexpr int kSmemBytes = kEpiOffset + 1024;
-  static constexpr int kTmemCols = 512;  // 2 x 256 accumulator columns per CTA
+  static constexpr int kTmemCols = 2 * TILE_N;  // double-buffered accumulator columns per CTA
 };
 
-template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, int SPIN = 0>
+// SPIN: 0 suspending try_wait, 1 spinning test_wait.  TILE_N: pair tile width.  MASKED: 9-operand MMA form.
+template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, int SPIN = 0, int TILE_N = 256, bool MASKED = false>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                      int K, const __grid_constant__ Epi epi) {
-  using Cfg = Gemm2Cfg<STAGES>;
+  using Cfg = Gemm2Cfg<STAGES, TILE_N>;
   static_assert(Epi::kPasses == 1, "2-CTA core supports single-pass epilogues");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -260,7 +275,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = umma_smem_desc(a_addr + k * kUmmaK * 2, kDescKMajorSW128);
             const uint64_t db = umma_smem_desc(b_addr + k * kUmmaK * 2, kDescKMajorSW128);
-            umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (MASKED)
+              umma_bf16_ss_2sm_masked(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage]);  // frees this stage in both CTAs
           if (++stage == STAGES) {
@@ -336,18 +354,28 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// Which SMs host the two CTAs of each cluster?  out[2 * cluster + rank] = %smid.  (cta_group::2 needs the two SMs of
+// one TPC; a cluster of 2 is the only placement control there is.)
+__global__ void cluster_smid_kernel(unsigned* out) {
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    out[2 * cluster_id_x() + cluster_ctarank()] = smid;
+  }
+}
+
 // Host launcher (cluster of 2 CTAs along x).  A: [M, K] bf16 row pitch lda; B: [N, K] bf16 row pitch ldb.
-template <int STAGES, bool M_FASTEST, int EPI_WARPS, int SPIN = 0, class Epi>
+template <int STAGES, bool M_FASTEST, int EPI_WARPS, int SPIN = 0, int TILE_N = 256, bool MASKED = false, class Epi>
 static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                                        const Epi& epi, int num_sms, cudaStream_t stream, int* pairs_out = nullptr) {
-  using Cfg = Gemm2Cfg<STAGES>;
+  using Cfg = Gemm2Cfg<STAGES, TILE_N>;
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   CUtensorMap tmA, tmB;
   if (make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBlockK, kBlockM) != 0)
     return cudaErrorInvalidValue;
   if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, Cfg::kTileN / 2) != 0)
     return cudaErrorInvalidValue;
-  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN>;
+  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN, TILE_N, MASKED>;
   const int smem_bytes = Cfg::kSmemBytes + Epi::smem_bytes(EPI_WARPS);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {

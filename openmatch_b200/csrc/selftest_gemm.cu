@@ -132,9 +132,10 @@ template <int BN, int STAGES, bool MF, int EW = 4>
 static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters);
 
 // 2-CTA (cta_group::2) core: same exact check
-template <int STAGES, bool MF, int EW>
+template <int STAGES, bool MF, int EW, int TILE_N = 256, bool MASKED = false>
 static int check_case2(int M, int N, int K, int num_sms) {
-  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, M, N, K);
+  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d tileN=%d masked=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, TILE_N,
+         (int)MASKED, M, N, K);
   fflush(stdout);
   std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
   std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
@@ -155,7 +156,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
-  cudaError_t e = launch_gemm2<STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  cudaError_t e = launch_gemm2<STAGES, MF, EW, 0, TILE_N, MASKED>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
   if (e != cudaSuccess) {
     printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
     return 1;
@@ -189,7 +190,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   return (bad || fault) ? 1 : 0;
 }
 
-template <int STAGES, bool MF, int EW, int SPIN = 0>
+template <int STAGES, bool MF, int EW, int SPIN = 0, int TILE_N = 256, bool MASKED = false>
 static void perf_case2(const char* name, int M, int N, int K, int num_sms, int iters) {
   __nv_bfloat16 *dA, *dB;
   unsigned long long* dcnt;
@@ -210,10 +211,10 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   int pairs = 0;
-  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -221,7 +222,7 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   ms /= iters;
   unsigned int fault = read_clear_dev_fault();
   double tf = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
-  printf("[perf 2sm spin=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", SPIN, name, STAGES,
+  printf("[perf 2sm spin=%d tileN=%d masked=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", SPIN, TILE_N, (int)MASKED, name, STAGES,
          (int)MF, EW, pairs, M, N, K, ms, tf, fault);
   fflush(stdout);
   cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
@@ -232,6 +233,37 @@ static int run_2sm(int sms) {
   fails += check_case2<6, false, 4>(256, 256, 64, sms);     // one pair tile, one k-block
   if (fails) return fails;                                  // nothing else can work
   fails += check_case2<6, false, 8>(300, 520, 192, sms);    // ragged edges, several tiles
+  fails += check_case2<6, false, 8, 128, false>(300, 520, 192, sms);  // 256 x 128 pair tiles
+  fails += check_case2<6, false, 8, 256, true>(300, 520, 192, sms);   // 9-operand MMA form
+  {  // TPC pairing of the clusters
+    unsigned* d_smid;
+    CK(cudaMalloc(&d_smid, 148 * 4));
+    CK(cudaMemset(d_smid, 0xff, 148 * 4));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (sms / 2));
+    cfg.blockDim = dim3(32);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, cluster_smid_kernel, d_smid));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned> h(148);
+    CK(cudaMemcpy(h.data(), d_smid, 148 * 4, cudaMemcpyDeviceToHost));
+    int same_tpc = 0, n = sms / 2;
+    for (int c = 0; c < n; ++c) same_tpc += (h[2 * c] / 2 == h[2 * c + 1] / 2) ? 1 : 0;
+    printf("[2sm] clusters whose CTAs sit on SMs 2t, 2t+1: %d of %d; first pairs:", same_tpc, n);
+    for (int c = 0; c < 6; ++c) printf(" (%u,%u)", h[2 * c], h[2 * c + 1]);
+    printf("\n");
+    cudaFree(d_smid);
+  }
+  // per-dispatch cost or per-byte cost?  256 x 128 pair tiles halve the FLOP and the peer-smem bytes per MMA
+  perf_case2<6, false, 8, 0, 128, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 0, 256, true>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 0, 128, true>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
   // one variable at a time: wait flavour (suspending try_wait vs spinning test_wait) x ring depth
   perf_case2<6, false, 8, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
   perf_case2<6, false, 8, 1>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
