@@ -499,6 +499,7 @@ int om_index_dim(const om_index* ix) { return ix ? ix->d : 0; }
 int om_index_reset(om_index* ix) {
   if (!ix) return fail(OM_EINVAL, "om_index_reset: null index");
   ix->n = 0;
+  ix->plan.valid = false;  // a search begun on the old contents cannot be finished
   return 0;
 }
 
