@@ -179,7 +179,10 @@ struct Gemm2Cfg {
 };
 
 // SPIN: 0 suspending try_wait, 1 spinning test_wait.  TILE_N: pair tile width.  MASKED: 9-operand MMA form.
-template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, int SPIN = 0, int TILE_N = 256, bool MASKED = false>
+// MODE (rate probes, results are garbage): 1 = MMA only (no TMA, the issuer never waits for operands),
+// 2 = loads only (the issuer waits and commits but issues no MMA).
+template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, int SPIN = 0, int TILE_N = 256, bool MASKED = false,
+          int MODE = 0>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                      int K, const __grid_constant__ Epi epi) {
@@ -230,7 +233,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_k = (K + kBlockK - 1) / kBlockK;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && MODE != 1) {
       // ------------------------------ TMA producer (both CTAs) ------------------------------
       uint32_t stage = 0, phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -267,7 +270,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * Cfg::kTileN;
         for (int kb = 0; kb < num_k; ++kb) {
-          wait2<SPIN>(&full_bar[stage], phase, 3);
+          if constexpr (MODE != 1) wait2<SPIN>(&full_bar[stage], phase, 3);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -275,10 +278,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = umma_smem_desc(a_addr + k * kUmmaK * 2, kDescKMajorSW128);
             const uint64_t db = umma_smem_desc(b_addr + k * kUmmaK * 2, kDescKMajorSW128);
-            if constexpr (MASKED)
+            if constexpr (MODE == 2) {
+              (void)da;
+              (void)db;
+            } else if constexpr (MASKED) {
               umma_bf16_ss_2sm_masked(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
+            } else {
               umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit_2sm(&empty_bar[stage]);  // frees this stage in both CTAs
           if (++stage == STAGES) {
@@ -365,7 +372,8 @@ __global__ void cluster_smid_kernel(unsigned* out) {
 }
 
 // Host launcher (cluster of 2 CTAs along x).  A: [M, K] bf16 row pitch lda; B: [N, K] bf16 row pitch ldb.
-template <int STAGES, bool M_FASTEST, int EPI_WARPS, int SPIN = 0, int TILE_N = 256, bool MASKED = false, class Epi>
+template <int STAGES, bool M_FASTEST, int EPI_WARPS, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0,
+          class Epi>
 static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                                        const Epi& epi, int num_sms, cudaStream_t stream, int* pairs_out = nullptr) {
   using Cfg = Gemm2Cfg<STAGES, TILE_N>;
@@ -375,7 +383,7 @@ static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B
     return cudaErrorInvalidValue;
   if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, Cfg::kTileN / 2) != 0)
     return cudaErrorInvalidValue;
-  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN, TILE_N, MASKED>;
+  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN, TILE_N, MASKED, MODE>;
   const int smem_bytes = Cfg::kSmemBytes + Epi::smem_bytes(EPI_WARPS);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {

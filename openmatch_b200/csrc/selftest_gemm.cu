@@ -190,7 +190,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   return (bad || fault) ? 1 : 0;
 }
 
-template <int STAGES, bool MF, int EW, int SPIN = 0, int TILE_N = 256, bool MASKED = false>
+template <int STAGES, bool MF, int EW, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0>
 static void perf_case2(const char* name, int M, int N, int K, int num_sms, int iters) {
   __nv_bfloat16 *dA, *dB;
   unsigned long long* dcnt;
@@ -211,10 +211,10 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   int pairs = 0;
-  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -222,7 +222,7 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   ms /= iters;
   unsigned int fault = read_clear_dev_fault();
   double tf = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
-  printf("[perf 2sm spin=%d tileN=%d masked=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", SPIN, TILE_N, (int)MASKED, name, STAGES,
+  printf("[perf 2sm spin=%d tileN=%d masked=%d mode=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", SPIN, TILE_N, (int)MASKED, MODE, name, STAGES,
          (int)MF, EW, pairs, M, N, K, ms, tf, fault);
   fflush(stdout);
   cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
@@ -260,6 +260,10 @@ static int run_2sm(int sms) {
     printf("\n");
     cudaFree(d_smid);
   }
+  // rate probes (garbage results): the pair-wide MMA alone, the 2-CTA TMA path alone
+  perf_case2<6, false, 8, 0, 256, false, 1>("8192^3 MMA only", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8, 0, 256, false, 2>("8192^3 loads only", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8, 0, 128, false, 1>("8192^3 MMA only", 8192, 8192, 8192, sms, 5);
   // per-dispatch cost or per-byte cost?  256 x 128 pair tiles halve the FLOP and the peer-smem bytes per MMA
   perf_case2<6, false, 8, 0, 128, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
   perf_case2<6, false, 8, 0, 256, true>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
