@@ -41,6 +41,7 @@ typedef enum { OM_REDUCE_MEAN = 0, OM_REDUCE_SUM = 1 } om_reduction;
 
 typedef struct om_encoder om_encoder;
 typedef struct om_index om_index;
+typedef struct om_comm om_comm;
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int om_abi_version(void);
@@ -95,7 +96,7 @@ int om_index_create(int d, om_index** out); /* faiss.IndexFlatIP(d); lives on th
 int om_index_add(om_index* idx, const void* x, om_memkind kind, om_dtype dtype, int64_t n, void* stream);
 /* Zero-copy ingest: reserve room for n more rows and get the device address of the fp32 row block
  * (row pitch = d floats) so the encoder can write embeddings in place; om_index_commit(n) publishes
- * them (builds the bf16 scan copy).  */
+ * them (builds the fp16 scan copy and updates the error-norm maxima the exactness certificate uses).  */
 int om_index_reserve(om_index* idx, int64_t n, float** dev_rows);
 int om_index_commit(om_index* idx, int64_t n, void* stream);
 int64_t om_index_ntotal(const om_index* idx);
@@ -104,16 +105,37 @@ int om_index_reset(om_index* idx);
 /* D, I = index.search(q, k): q [nq, d] fp32 (host or device); D fp32 [nq, k], I int64 [nq, k] written to
  * host or device memory (out_kind).  Rows are ordered by (score descending, id ascending); missing
  * slots (k > ntotal) hold id -1 and score -FLT_MAX, as faiss does.  Reported ids are id_offset + local
- * row, so a rank of a row-sharded index passes the global id of its first row.  Scores are exact fp32
- * inner products (candidates are selected on bf16 tensor-core scores with a safety margin, then
- * re-scored in fp32).  Synchronous with respect to `stream` on return. */
+ * row, so a rank of a row-sharded index passes the global id of its first row.  k <= 4096.
+ * Exactness: candidates (k + slack per query) are selected on fp16 tensor-core scores and re-scored in fp32;
+ * an a-posteriori certificate (measured quantisation-error norms of corpus and query, see csrc/search.cu
+ * certify_kernel) then PROVES per query that no row outside the candidate list can reach the k-th fp32 score.
+ * Queries that fail it are re-run with the widest candidate list (4096) and, if still unproven (e.g. thousands
+ * of near-duplicate rows), answered by an exact fp32 scan with the same summation order as the re-score.  The
+ * result is therefore always the exact top-k by fp32 inner product with ties by ascending id.
+ * Synchronous with respect to `stream` on return. */
 int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
                     om_memkind out_kind, int64_t id_offset, void* stream);
+/* Row-sharded search with the exchange inside the library — replaces faiss.index_cpu_to_gpu_multiple(shard=True) +
+ * IndexShards (src/openmatch/retriever/dense_retriever.py:43-58).  One process per GPU; every rank holds a contiguous
+ * row shard and calls om_index_search_sharded with the same queries and its own id_offset; every rank receives the
+ * same global (D, I).  All collectives (NCCL over NVLink: MAX all-reduce of the per-query score range, SUM all-reduce
+ * of a 256-bin histogram, one packed all-gather of a fixed-width prefix of the per-shard lists) are issued on `stream`
+ * between the kernels, with a single host synchronisation at the end; exactness is certified as in om_index_search.
+ *   om_comm_unique_id : rank 0 obtains 128 opaque bytes (ncclGetUniqueId) and ships them to the other ranks
+ *                       (e.g. torch.distributed.broadcast_object_list)
+ *   om_comm_init      : collective over the `world` ranks (ncclCommInitRank) on the current device
+ * NCCL is bound at run time (dlopen of libnccl.so.2; inside PyTorch that is the copy torch already loaded). */
+int om_comm_unique_id(char* out128);
+int om_comm_init(const char* unique_id128, int rank, int world, om_comm** out);
+void om_comm_destroy(om_comm* comm);
+int om_index_search_sharded(om_index* idx, om_comm* comm, const void* q, om_memkind q_kind, int nq, int k, float* D,
+                            int64_t* I, om_memkind out_kind, int64_t id_offset, void* stream);
+
 /* Three-phase variant for row-sharded indexes (one shard per process, at most 16384 queries per round trip).
  * Replaces the per-shard full top-k that faiss IndexShards computes before merging (dense_retriever.py:43-58):
  * the shards agree on a per-query score floor first, so each one re-scores and ships ~k / n_shards rows.
- *   begin : bf16 scan of the local shard.  local_range (device fp32 [2, nq]) receives per query the local
- *           (k + slack)-th best bf16-stage score (row 0; -inf when the shard has fewer rows) and the local best
+ *   begin : fp16 tensor-core scan of the local shard.  local_range (device fp32 [2, nq]) receives per query the local
+ *           (k + slack)-th best candidate-stage score (row 0; -inf when the shard has fewer rows) and the local best
  *           (row 1).  The caller MAX-reduces it over the shards.
  *   count : local_hist (device int32 [nq, om_search_floor_bins()]) receives the histogram of the local
  *           candidates over equal-width bins of [global_range[0][q], global_range[1][q]].  The caller SUM-reduces.
@@ -121,21 +143,28 @@ int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int
  *           score (every member of the global top-k is among them) and writes them sorted to device D fp32
  *           [nq, k] / I int64 [nq, k], padded with -FLT_MAX / -1.  global_hist == NULL: floor = global_range[0];
  *           global_range == NULL: no pruning.  kept_max (device int32, nullable) receives the longest valid prefix
- *           over the queries, so the caller can exchange [nq, kept_max] instead of [nq, k]. */
+ *           over the queries, so the caller can exchange [nq, kept_max] instead of [nq, k].
+ * These are the uncertified building blocks (the caller reduces between the phases, e.g. over gloo in the CPU
+ * protocol test); om_index_search_sharded runs the same phases plus the certificate and its escalation. */
 int om_index_search_begin(om_index* idx, const void* q, om_memkind q_kind, int nq, int k, float* local_range,
                           void* stream);
 int om_index_search_count(om_index* idx, const float* global_range, int* local_hist, void* stream);
 int om_index_search_finish(om_index* idx, const float* global_range, const int* global_hist, float* D, int64_t* I,
                            int64_t id_offset, int* kept_max, void* stream);
 int om_search_floor_bins(void);
-/* Tunables: "rescore_slack" (extra bf16-stage candidates kept per query; default max(64, k/8)),
+/* Tunables: "rescore_slack" (extra candidate-stage rows kept per query; default max(128, k/5)),
  * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing),
  * "round_growth" (2..8, default 2: each scan round covers (g-1) x the rows already seen),
+ * "certify" (default 1; 0 = skip the exactness certificate and its escalation: top-k of the fp16 candidate stage),
+ * "exact_only" (1 = answer every query with the exact fp32 CUDA-core scan; testing),
+ * "debug_stage_scores" (1 = D holds candidate-stage scores instead of fp32 re-scores; error-model measurement),
  * "profile" (1 = bracket every kernel launch of a search with CUDA events on the launching stream). */
 int om_index_set_param(om_index* idx, const char* name, int64_t value);
 /* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity),
- * "launches" (kernels launched), and with "profile" on: "scan_ns", "select_ns", "finalize_ns" (device time
- * summed over the launches of each kind). */
+ * "launches" (kernels launched), "uncertified" (queries the first level could not prove exact),
+ * "uncertified_wide" (still unproven with 4096 candidates), "exact_queries" (answered by the exact fp32 scan),
+ * "wide_exchanges" (sharded levels redone at full exchange width), and with "profile" on: "scan_ns", "select_ns",
+ * "finalize_ns", "other_ns" (device time summed over the launches of each kind; other = exchange + merge + certify). */
 int64_t om_index_get_stat(const om_index* idx, const char* name);
 void om_index_destroy(om_index* idx);
 
@@ -144,7 +173,8 @@ void om_index_destroy(om_index* idx);
  * ids < 0 are padding.  Matches merge semantics of faiss IndexShards / utils.py:215-229. */
 int om_topk_merge(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k, float* D, int64_t* I,
                   void* stream);
-/* Same with input lists of width k_in (e.g. the kept_max prefix of om_index_search_finish) and k_out results. */
+/* Same with input lists of width k_in (e.g. the kept_max prefix of om_index_search_finish) and k_out results;
+ * more than 8192 entries per query (nparts * k_in) are merged hierarchically. */
 int om_topk_merge_n(const float* D_parts, const int64_t* I_parts, int nparts, int nq, int k_in, int k_out, float* D,
                     int64_t* I, void* stream);
 

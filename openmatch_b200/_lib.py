@@ -47,6 +47,11 @@ SIGNATURES = {
     "om_index_reset": (c_int, [c_void_p]),
     "om_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int64,
                                 c_void_p]),
+    "om_comm_unique_id": (c_int, [c_void_p]),
+    "om_comm_init": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "om_comm_destroy": (None, [c_void_p]),
+    "om_index_search_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                        c_int64, c_void_p]),
     "om_index_search_begin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "om_index_search_count": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "om_index_search_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

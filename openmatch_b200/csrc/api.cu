@@ -17,6 +17,12 @@ int device_sm_count() {
     return fail(OM_ENODEVICE, "no CUDA device available: %s (this library has no CPU path)", cudaGetErrorString(e));
   }
   if (dev == cached_dev) return cached_sms;
+  // Launcher state (tile-counter pool, loss workspace, one-time cudaFuncSetAttribute guards) is per process and
+  // therefore per device: one process drives ONE GPU (torchrun's model).  A second device is refused loudly
+  // instead of launching with another device's buffers / missing shared-memory opt-ins.
+  if (cached_dev >= 0)
+    return fail(OM_ESTATE, "libopenmatch_b200 is bound to CUDA device %d in this process; device %d is current "
+                "(one process per GPU)", cached_dev, dev);
   cudaDeviceProp p;
   e = cudaGetDeviceProperties(&p, dev);
   if (e != cudaSuccess) {

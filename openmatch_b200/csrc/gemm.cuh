@@ -58,7 +58,7 @@ struct GemmCfg {
 //        its overflow path when a thread finds more survivors than its stash holds)
 // Rows >= M and columns >= N contain zeros (TMA out-of-bounds fill) and must be masked by the functor.
 
-template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
+template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, bool F16 = false>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, const __grid_constant__ Epi epi, int* tile_counter) {
@@ -158,7 +158,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------ MMA issuer ------------------------------
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+      // F16: both operands IEEE half instead of bf16 (same instruction, same rate, 3 more significand bits)
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(kBlockM, BN) : umma_idesc_bf16(kBlockM, BN);
       uint32_t stage = 0, phase = 0, sslot = 0, sphase = 0;
       int it = 0;
       for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
@@ -311,7 +312,7 @@ static inline int* next_tile_counter(cudaStream_t stream) {
 // the static order CTAs drift apart over thousands of tiles and stop sharing operand tiles in L2 (measured on
 // the search scan: 143 GB of DRAM reads for a 6.4 GB shard); the dynamic order keeps all CTAs on neighbouring
 // tiles.
-template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi>
+template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, bool F16 = false>
 static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                                       const Epi& epi, int num_sms, cudaStream_t stream, bool dynamic_sched = false) {
   using Cfg = GemmCfg<BN, STAGES>;
@@ -321,7 +322,7 @@ static inline cudaError_t launch_gemm(const void* A, int64_t lda, const void* B,
     return cudaErrorInvalidValue;
   if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, BN) != 0)
     return cudaErrorInvalidValue;
-  auto kern = gemm_bf16_tn_kernel<BN, STAGES, M_FASTEST, EPI_WARPS, Epi>;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, M_FASTEST, EPI_WARPS, Epi, F16>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

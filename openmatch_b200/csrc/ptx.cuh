@@ -261,6 +261,10 @@ constexpr uint64_t kDescKMajorSW128 = umma_smem_desc_base(16, 1024, kSwizzle128B
 // Instruction descriptor for kind::f16 with BF16 A/B, FP32 accumulate.
 //   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt  [15] A major (0=K)  [16] B major
 //   [17,23) N>>3   [24,29) M>>4
+// A and B in IEEE fp16 (format code 0), fp32 accumulate, K-major operands
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major = 0,
                                                        uint32_t b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |

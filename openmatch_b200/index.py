@@ -89,6 +89,27 @@ class FlatIPIndex:
                                              I.data_ptr(), _lib.OM_DEVICE, int(id_offset), _stream()))
         return D, I
 
+    def search_sharded_device(self, comm: "Comm", q: torch.Tensor, k: int, id_offset: int = 0):
+        """This rank's call of the row-sharded search (``om_index_search_sharded``): collective over ``comm``; every
+        rank passes the same queries and receives the same global (D, I) [nq, k] on its device."""
+        q = q.contiguous().float()
+        self._check_shape(q.shape)
+        nq = q.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        _lib.check(self._lib.om_index_search_sharded(self._h, comm._h, q.data_ptr(), _lib.OM_DEVICE, nq, int(k),
+                                                     D.data_ptr(), I.data_ptr(), _lib.OM_DEVICE, int(id_offset), _stream()))
+        return D, I
+
+    def search_sharded_pinned(self, comm: "Comm", q_host: torch.Tensor, k: int, D_out: torch.Tensor, I_out: torch.Tensor,
+                              id_offset: int = 0) -> None:
+        """Host (pinned) queries in; results into ``D_out`` / ``I_out`` (pinned host on the rank that wants them,
+        device tensors elsewhere)."""
+        nq = q_host.shape[0]
+        kind = _lib.OM_DEVICE if D_out.is_cuda else _lib.OM_HOST
+        _lib.check(self._lib.om_index_search_sharded(self._h, comm._h, q_host.data_ptr(), _lib.OM_HOST, nq, int(k),
+                                                     D_out.data_ptr(), I_out.data_ptr(), kind, int(id_offset), _stream()))
+
     def search_begin(self, q: torch.Tensor, k: int) -> torch.Tensor:
         """Phase 1 of the sharded search: bf16 scan of the local shard; returns the per-query (local floor, local
         best) bf16-stage scores as a CUDA fp32 [2, nq] tensor, to be MAX-reduced over the shards."""
@@ -175,6 +196,43 @@ def _wrap_device_f32(ptr: int, shape) -> torch.Tensor:
     return torch.as_tensor(_CudaArrayView(ptr, shape), device="cuda")
 
 
+class Comm:
+    """NCCL communicator owned by libopenmatch_b200 for the row-sharded search (``om_comm_init``).  The 128-byte
+    unique id is created on rank 0 and shipped to the other ranks of the torch.distributed ``group`` (any backend),
+    then every rank joins collectively on its current CUDA device."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._lib = _lib.load()
+        self._h = None
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        uid = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(self._lib.om_comm_unique_id(uid))
+        box = [uid.raw]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.om_comm_init(ctypes.create_string_buffer(box[0], 128), self.rank, self.world, ctypes.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.om_comm_destroy(h)
+
+
+_COMMS = {}
+
+
+def comm_for(group=None):
+    """One library communicator per process group (created collectively on first use)."""
+    key = id(group) if group is not None else 0
+    if key not in _COMMS:
+        _COMMS[key] = Comm(group)
+    return _COMMS[key]
+
+
 def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """[nparts, nq, k_in] per-shard results (shards in increasing id order) -> global (D, I) [nq, k]."""
     lib = _lib.load()
@@ -190,7 +248,10 @@ def merge_topk_device(D_parts: torch.Tensor, I_parts: torch.Tensor, k: int) -> T
 
 
 def sharded_search_device(index: "FlatIPIndex", q: torch.Tensor, k: int, id_offset: int, group=None, merge=None):
-    """Row-sharded exact search, this rank's part + the exchange (NCCL over NVLink):
+    """Row-sharded exact search.  With a real ``FlatIPIndex`` on a NCCL process group the whole sequence (scan,
+    collectives, re-score, merge, exactness certificate) runs inside the library on the current stream
+    (``om_index_search_sharded``).  Otherwise — the CPU protocol test drives this function under gloo with the
+    oracle's restatement of the phases — the same phases are stepped from Python:
       1. bf16 scan of the local shard                                    -> (floor, best) per query
       2. all-reduce MAX [2, nq]; local histogram over the agreed range   -> all-reduce SUM [nq, 64]
       3. fp32 re-score of the local candidates above the global floor (~k / world rows per query, not k)
@@ -199,7 +260,11 @@ def sharded_search_device(index: "FlatIPIndex", q: torch.Tensor, k: int, id_offs
     ``index`` only needs ``search_begin / search_count / search_finish`` (tests run this function on CPU under
     gloo with the oracle's restatement of the three phases and the oracle's ``merge``)."""
     import torch.distributed as dist
-    if not dist.is_initialized() or dist.get_world_size(group) == 1 or q.shape[0] > 16384:
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return index.search_device(q, k, id_offset=id_offset)
+    if isinstance(index, FlatIPIndex) and merge is None and dist.get_backend(group) == "nccl":
+        return index.search_sharded_device(comm_for(group), q, k, id_offset)
+    if q.shape[0] > 16384:
         D, I = index.search_device(q, k, id_offset=id_offset)
         return exchange_and_merge(D, I, k, group, merge)
     rng = index.search_begin(q, k)

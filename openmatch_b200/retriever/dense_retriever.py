@@ -148,7 +148,9 @@ class Retriever:
         for i, part in enumerate(files):
             with open(part, "rb") as f:
                 encoded, lookup = pickle.load(f)
-            if i == 0 or self.index is None:
+            # (The reference re-creates its index on the first file of every call, :102-103; a rank of a row-sharded
+            # retriever calls this once per file it owns, so rows must accumulate — start afresh with reset_index().)
+            if self.index is None or self.index.d != encoded.shape[1]:
                 self._initialize_faiss_index(encoded.shape[1])
             self.index.add(encoded)
             self.doc_lookup.extend(lookup)

@@ -40,8 +40,9 @@ class _ShardByBatch(IterableDataset):
                 yield from pending[self.rank * self.per_device:(self.rank + 1) * self.per_device]
                 pending = []
         if pending:  # pad the tail cyclically so every rank sees the same number of batches
+            n0 = len(pending)
             while len(pending) < group:
-                pending.append(pending[len(pending) % max(1, len(pending))])
+                pending.append(pending[len(pending) % n0])
             yield from pending[self.rank * self.per_device:(self.rank + 1) * self.per_device]
 
 

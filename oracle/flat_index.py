@@ -114,28 +114,28 @@ class ShardPhases:
     ``om_index_search_begin / _count / _finish``), used to check the protocol's host logic under gloo.
 
     The role is the one faiss ``IndexShards`` plays behind ``index_cpu_to_gpu_multiple(shard=True)``
-    (dense_retriever.py:43-58); the protocol itself is ours: a candidate stage on bf16-rounded operands keeps
+    (dense_retriever.py:43-58); the protocol itself is ours: a candidate stage on fp16-rounded operands keeps
     the local top-kp, the shards agree on a per-query floor through a MAX-reduced (floor, best) range and a
     SUM-reduced histogram, and only candidates in or above the bin holding the global kp-th score are re-scored
     in fp32 and exchanged.  Tensors in / out are torch CPU tensors so that ``torch.distributed`` can reduce them.
     """
 
-    def __init__(self, x: np.ndarray, slack: int = 64):
+    def __init__(self, x: np.ndarray, slack: int = 128):
         self.x = np.ascontiguousarray(x, dtype=np.float32)
         self.slack = slack
 
     @staticmethod
-    def _bf16(a: np.ndarray) -> np.ndarray:
-        import torch
-        return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).float().numpy()
+    def _f16(a: np.ndarray) -> np.ndarray:
+        """IEEE half rounding of the scan operands (csrc/search.cu rows_to_f16_kernel; finite values saturate)"""
+        return np.clip(np.ascontiguousarray(a, np.float32), -65504.0, 65504.0).astype(np.float16).astype(np.float32)
 
     def search_begin(self, q, k: int):
         import torch
         self.q = np.ascontiguousarray(q.numpy() if hasattr(q, "numpy") else q, dtype=np.float32)
         self.k = k
-        self.kp_target = k + max(self.slack, k // 8)
+        self.kp_target = min(k + max(self.slack, k // 5), 4096)
         kp = min(self.kp_target, self.x.shape[0])
-        s = self._bf16(self.q) @ self._bf16(self.x).T if self.x.shape[0] else np.zeros((self.q.shape[0], 0), np.float32)
+        s = self._f16(self.q) @ self._f16(self.x).T if self.x.shape[0] else np.zeros((self.q.shape[0], 0), np.float32)
         self.cand_s, self.cand_i = _topk_rows(s.astype(np.float32), kp) if kp else (s, s.astype(np.int64))
         nq = self.q.shape[0]
         rng = np.full((2, nq), -np.inf, np.float32)
