@@ -282,10 +282,17 @@ def main():
             acc[key] += idx.stat(key)
         rounds = idx.stat("rounds")
 
-    for _ in range(args.warmup):
-        search_step(q_dev)
-    with ClockSampler(local_rank) as clocks:
-        total_ms = timed(value_step, args.steps, 0)
+    step_wall = []
+
+    def value_step_timed():
+        t0 = time.perf_counter()
+        value_step()
+        step_wall.append((time.perf_counter() - t0) * 1e3)  # host wall per step (diagnostic; every step ends synchronised)
+
+    with ClockSampler(local_rank) as clocks:  # started before the warm-up: nvidia-smi's start-up lands outside the timed steps
+        for _ in range(args.warmup):
+            search_step(q_dev)
+        total_ms = timed(value_step_timed, args.steps, 0)
     idx.set_param("profile", 0)
     ms_per_step = total_ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
@@ -389,6 +396,7 @@ def main():
                         "exact_scan_queries_per_step": acc["exact_queries"] / args.steps,
                         "wide_exchanges": acc["wide_exchanges"], "overflow_retries": acc["overflow_retries"]},
         "clocks": clocks.summary(),
+        "step_wall_ms": step_wall,
     }
     if parity is not None:
         line["parity"] = parity

@@ -154,6 +154,34 @@ class DRModel(nn.Module):
             reps = F.normalize(reps, dim=1)
         return hidden, reps
 
+    @torch.no_grad()
+    def encode_into(self, items, out: Tensor, is_query: bool = False) -> Tensor:
+        """Inference only: representations of ``items`` written IN PLACE into ``out`` (fp32 / bf16 ``[B, rep_dim]``
+        CUDA tensor with unit column stride — e.g. the rows ``FlatIPIndex.reserve_rows`` handed out), no
+        intermediate ``[B, d]`` tensor and no copy.  Same arithmetic as ``encode`` (:133-155)."""
+        model, head = (self.lm_q, self.head_q) if is_query else (self.lm_p, self.head_p)
+        input_ids = items["input_ids"]
+        if not input_ids.is_cuda:
+            raise RuntimeError("openmatch_b200 encodes on a CUDA device only (no CPU path): move the batch to GPU")
+        enc = self._cuda_encoder(model, head)
+        B, L = input_ids.shape
+        if out.shape[0] != B or out.shape[1] != enc.rep_dim:
+            raise ValueError("out must be [%d, %d], got %s" % (B, enc.rep_dim, tuple(out.shape)))
+        max_b = max(1, enc.max_batch_tokens // L)
+        tt = items.get("token_type_ids", None)
+        for lo in range(0, B, max_b):
+            sl = slice(lo, lo + max_b)
+            enc.encode(input_ids[sl], items["attention_mask"][sl], tt[sl] if tt is not None else None, out=out[sl])
+        return out
+
+    def rep_dim(self, is_query: bool = False) -> int:
+        """width of the representations ``encode`` produces (head output, else the backbone's hidden size)"""
+        head = self.head_q if is_query else self.head_p
+        if head is not None:
+            return int(head.linear.weight.shape[0])
+        lm = self.lm_q if is_query else self.lm_p
+        return int(getattr(lm.config, "hidden_size", None) or lm.config.d_model)
+
     def encode_passage(self, psg):
         return self.encode(psg, self.lm_p, self.head_p)
 

@@ -29,6 +29,7 @@ from tqdm import tqdm
 
 from ..arguments import InferenceArguments as EncodingArguments
 from ..dataset import DRInferenceCollator
+from ..embedding_store import EmbeddingFile, write_embedding_file
 from ..index import FlatIPIndex, shard_offsets, sharded_search_device
 from ..modeling import DRModelForInference
 from ..utils import merge_retrieval_results_by_score
@@ -102,16 +103,26 @@ class Retriever:
                           num_workers=self.args.dataloader_num_workers, pin_memory=self.args.dataloader_pin_memory)
 
     def _encode_dataset(self, dataset, is_query: bool, into_index: bool):
-        """Shared encode loop: H2D of the int64 id tensors, CUDA encoder, embeddings stay on the device."""
+        """Shared encode loop: H2D of the id tensors, CUDA encoder, embeddings stay on the device.  With
+        ``into_index`` the encoder writes its output rows IN PLACE into this rank's index shard
+        (``reserve_rows`` -> ``DRModel.encode_into`` -> ``commit_rows``: no intermediate tensor, no copy).
+        Datasets that can hand out whole ``[B, L]`` blocks (``PretokenizedDataset.iter_batches``) skip the per-example
+        DataLoader / collator path altogether."""
+        if hasattr(dataset, "iter_batches") and hasattr(self.model, "encode_into"):
+            return self._encode_blocks(dataset, is_query, into_index)
         ids: List[str] = []
         chunks: List[torch.Tensor] = []
         device = self.args.device
+        in_place = into_index and hasattr(self.model, "encode_into")
         for batch_ids, batch in tqdm(self._loader(dataset), disable=self.args.local_process_index > 0):
             ids.extend(batch_ids)
             batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
+            if in_place:
+                self._encode_rows_in_place(batch, is_query)
+                continue
             out = self.model(query=batch) if is_query else self.model(passage=batch)
             reps = out.q_reps if is_query else out.p_reps
-            if into_index:
+            if into_index:  # foreign model object without encode_into: one device-to-device copy
                 if self.index is None:
                     self._initialize_faiss_index(reps.shape[1])
                 rows = self.index.reserve_rows(reps.shape[0])
@@ -119,6 +130,48 @@ class Retriever:
                 self.index.commit_rows(reps.shape[0])
             else:
                 chunks.append(reps.float())
+        return ids, chunks
+
+    def _encode_rows_in_place(self, batch, is_query: bool):
+        if self.index is None:
+            self._initialize_faiss_index(self.model.rep_dim(is_query))
+        n = batch["input_ids"].shape[0]
+        rows = self.index.reserve_rows(n)
+        self.model.encode_into(batch, rows, is_query)
+        self.index.commit_rows(n)
+
+    def _encode_blocks(self, dataset, is_query: bool, into_index: bool):
+        """Block ingest: memory-mapped int32 ``[b, L]`` slice -> pinned staging buffer (double-buffered) -> async H2D
+        -> int64 ids + mask built on the device -> encoder (-> index rows in place)."""
+        device = self.args.device
+        ids: List[str] = []
+        chunks: List[torch.Tensor] = []
+        bs, L = dataset.batch_size, dataset.max_len
+        stage = [torch.empty((bs, L), dtype=torch.int32).pin_memory() for _ in range(2)]
+        busy = [None, None]
+        if into_index:
+            if self.index is None:
+                self._initialize_faiss_index(self.model.rep_dim(is_query))
+            if hasattr(dataset, "num_local_rows"):
+                self.index.reserve_rows(dataset.num_local_rows())  # capacity only: no re-allocation while encoding
+        dim = self.model.rep_dim(is_query)
+        for bi, (names, block) in enumerate(tqdm(dataset.iter_batches(), disable=self.args.local_process_index > 0)):
+            slot = bi & 1
+            if busy[slot] is not None:
+                busy[slot].synchronize()  # the H2D copy that last read this pinned buffer has finished
+            n = block.shape[0]
+            np.copyto(stage[slot][:n].numpy(), block)
+            d_ids = stage[slot][:n].to(device, non_blocking=True)
+            busy[slot] = torch.cuda.Event()
+            busy[slot].record()
+            batch = {"input_ids": d_ids.long(), "attention_mask": (d_ids != 0).long()}
+            ids.extend(names)
+            if into_index:
+                self._encode_rows_in_place(batch, is_query)
+            else:
+                out = torch.empty((n, dim), dtype=torch.float32, device=device)
+                self.model.encode_into(batch, out, is_query)
+                chunks.append(out)
         return ids, chunks
 
     # ------------------------------------------------------------------ corpus side
@@ -129,10 +182,14 @@ class Retriever:
         self.doc_lookup = list(ids)
         self._resident_rows = len(ids)
         os.makedirs(self.args.output_dir, exist_ok=True)
-        encoded = self._index_rows_to_host()
-        with open(os.path.join(self.args.output_dir, "embeddings.corpus.rank.{}".format(self.args.process_index)), "wb") as f:
-            pickle.dump((encoded, ids), f, protocol=4)
-        del encoded
+        path = os.path.join(self.args.output_dir, "embeddings.corpus.rank.{}".format(self.args.process_index))
+        if self.index is None or self.index.ntotal == 0:
+            with open(path, "wb") as f:
+                pickle.dump((np.zeros((0, 0), dtype=np.float32), ids), f, protocol=4)
+        else:
+            # same bytes-on-disk contract as the reference's pickle.dump((encoded, lookup), protocol=4) (:84-86), but the
+            # shard is streamed out of HBM through one pinned chunk instead of materialising [n, d] twice on the host
+            write_embedding_file(path, self.index.master_rows(), ids)
         if self.args.world_size > 1:
             torch.distributed.barrier()
 
@@ -146,13 +203,19 @@ class Retriever:
         files = [partition] if partition is not None else sorted(
             glob.glob(os.path.join(self.args.output_dir, "embeddings.corpus.rank.*")))
         for i, part in enumerate(files):
-            with open(part, "rb") as f:
-                encoded, lookup = pickle.load(f)
+            # reference: pickle.load of the whole (matrix, ids) tuple (:96-101); here the matrix payload is memory-mapped
+            # and fed to the index chunk by chunk (files written by the reference, by us or by split_embeddings.py)
+            ef = EmbeddingFile(part)
+            encoded, lookup = ef, ef.ids
             # (The reference re-creates its index on the first file of every call, :102-103; a rank of a row-sharded
             # retriever calls this once per file it owns, so rows must accumulate — start afresh with reset_index().)
+            if ef.shape[0] == 0:
+                continue
             if self.index is None or self.index.d != encoded.shape[1]:
                 self._initialize_faiss_index(encoded.shape[1])
-            self.index.add(encoded)
+            self.index.reserve_rows(ef.shape[0])  # capacity for the whole file: one allocation
+            for chunk in ef.chunks():
+                self.index.add(np.ascontiguousarray(chunk))
             self.doc_lookup.extend(lookup)
 
     @classmethod

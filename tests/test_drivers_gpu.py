@@ -150,3 +150,85 @@ def test_grad_cache_matches_plain_step(workdir):
     l1, g1 = grads(GCDenseTrainer, grad_cache=True, gc_q_chunk_size=3, gc_p_chunk_size=8)
     assert abs(l0 - l1) <= 1e-3 * max(1.0, abs(l0))
     assert np.linalg.norm(g0 - g1) <= 2e-2 * np.linalg.norm(g0)
+
+
+def test_hard_negative_mining_loop_with_untied_encoders(workdir):
+    """docs/dr-msmarco-passage.md:98-157 end to end: train (untied query / passage encoders) -> build_index -> retrieve
+    over the TRAIN queries -> build_hn -> second training round on the mined shards.  Also checks the untied checkpoint
+    layout (dense_retrieval_model.py:189-213,230-245) and that the two towers really differ after training."""
+    from transformers import BertTokenizer
+
+    from openmatch.arguments import ModelArguments
+    from openmatch.driver import build_hn, build_index, retrieve, train_dr
+    from openmatch.modeling import DRModelForInference
+    from openmatch.utils import load_from_trec
+    tok = BertTokenizer(str(workdir / "vocab.txt"), do_lower_case=True)
+    ckpt = workdir / "ckpt_untied"
+    _run(train_dr.main, ["--output_dir", ckpt, "--model_name_or_path", workdir / "model", "--do_train", "--untie_encoder",
+                         "--train_path", workdir / "train.jsonl", "--per_device_train_batch_size", 4,
+                         "--train_n_passages", 4, "--learning_rate", "1e-3", "--q_max_len", 8, "--p_max_len", 16,
+                         "--max_steps", 4, "--logging_steps", 2, "--save_steps", 1000, "--bf16",
+                         "--dataloader_num_workers", 0])
+    cfg = json.load(open(ckpt / "openmatch_config.json"))
+    assert cfg["tied"] is False
+    assert os.path.exists(ckpt / "query_model" / "config.json") and os.path.exists(ckpt / "passage_model" / "config.json")
+    model = DRModelForInference.build(ModelArguments(model_name_or_path=str(ckpt)))
+    assert model.lm_q is not model.lm_p and not model.tied
+    wq = model.lm_q.encoder.layer[0].attention.self.query.weight
+    wp = model.lm_p.encoder.layer[0].attention.self.query.weight
+    assert not torch.equal(wq, wp), "towers did not diverge"
+    ids = torch.tensor([[2, 9, 10, 11, 3, 0, 0, 0]]).cuda()
+    batch = {"input_ids": ids, "attention_mask": (ids != 0).long(), "token_type_ids": torch.zeros_like(ids)}
+    model = model.cuda().eval()
+    rq, rp = model(query=batch).q_reps, model(passage=batch).p_reps
+    assert not torch.allclose(rq, rp, atol=1e-3), "query and passage towers give identical representations"
+    del model
+
+    emb = workdir / "emb_hn"
+    common = ["--output_dir", emb, "--model_name_or_path", ckpt, "--per_device_eval_batch_size", 16, "--q_max_len", 8,
+              "--p_max_len", 32, "--dataloader_num_workers", 0]
+    _run(build_index.main, common + ["--corpus_path", workdir / "corpus.tsv", "--doc_template", "<title> <text>",
+                                     "--doc_column_names", "id,title,text"])
+    run = workdir / "train.trec"
+    _run(retrieve.main, common + ["--query_path", workdir / "queries.tsv", "--query_template", "<text>",
+                                  "--query_column_names", "id,text", "--trec_save_path", run, "--retrieve_depth", 30,
+                                  "--use_gpu"])
+    ranked = load_from_trec(str(run))
+    # qrels: pretend the 3rd-ranked passage of every train query is its positive
+    with open(workdir / "qrels.tsv", "w") as f:
+        for q, docs in ranked.items():
+            f.write("%s\t0\t%s\t1\n" % (q, list(docs)[2]))
+    # pre-tokenised stores (text preprocessing is upstream of this tier's scope)
+    def store(path_tsv, stem, text_cols):
+        names, rows = [], []
+        for line in open(path_tsv):
+            parts = line.rstrip("\n").split("\t")
+            names.append(parts[0])
+            rows.append(tok.encode(" ".join(parts[c] for c in text_cols), add_special_tokens=False)[:32])
+        arr = np.zeros((len(rows), 32), np.int32)
+        for i, r in enumerate(rows):
+            arr[i, : len(r)] = r
+        np.save(workdir / (stem + ".npy"), arr)
+        (workdir / (stem + ".ids.txt")).write_text("\n".join(names))
+    store(workdir / "corpus.tsv", "collection_tok", (1, 2))
+    store(workdir / "queries.tsv", "queries_tok", (1,))
+    hn = workdir / "hn"
+    _run(build_hn.main, ["--hn_file", run, "--qrels", workdir / "qrels.tsv", "--queries", workdir / "queries_tok.npy",
+                         "--collection", workdir / "collection_tok.npy", "--save_to", hn, "--n_sample", 5, "--depth", 20,
+                         "--seed", 3])
+    rows = [json.loads(line) for line in open(hn / "split00.hn.jsonl")]
+    assert len(rows) == len(ranked)
+    col = np.load(workdir / "collection_tok.npy")
+    col_ids = (workdir / "collection_tok.ids.txt").read_text().split("\n")
+    doc_tok = {n: col[i][col[i] != 0].tolist() for i, n in enumerate(col_ids)}
+    for (q, docs), r in zip(ranked.items(), rows):
+        pos = list(docs)[2]
+        assert r["positives"] == [doc_tok[pos]] and len(r["negatives"]) == 5
+        allowed = [doc_tok[d] for d in [d for d in docs if d != pos][:20]]  # first `depth` non-relevant passages of the run
+        assert all(n in allowed for n in r["negatives"]) and doc_tok[pos] not in r["negatives"]
+    ckpt2 = workdir / "ckpt_round2"
+    _run(train_dr.main, ["--output_dir", ckpt2, "--model_name_or_path", ckpt, "--do_train", "--train_dir", hn,
+                         "--per_device_train_batch_size", 4, "--train_n_passages", 4, "--learning_rate", "1e-3",
+                         "--q_max_len", 8, "--p_max_len", 16, "--max_steps", 3, "--logging_steps", 1, "--save_steps", 1000,
+                         "--bf16", "--dataloader_num_workers", 0])
+    assert json.load(open(ckpt2 / "openmatch_config.json"))["tied"] is False

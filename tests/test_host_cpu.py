@@ -198,3 +198,34 @@ def test_rank_arrays_and_vectorised_trec_writer_match_the_dict_path(tmp_path):
     dup.save_trec(str(tmp_path / "dup.trec"))
     utils.save_as_trec(_results_dict(["q0"], np.array(["a", "b", "a"]), dup.D, dup.I), str(tmp_path / "dup2.trec"))
     assert (tmp_path / "dup.trec").read_bytes() == (tmp_path / "dup2.trec").read_bytes()
+
+
+def test_pretokenized_block_iterator_matches_the_per_example_iterator(tmp_path):
+    # PretokenizedDataset.iter_batches (whole [B, L] int32 slices, the ingest path of Retriever) must hand out exactly the
+    # examples, ids and rank interleaving of the reference-style per-example iterator (inference_dataset.py:99-115)
+    from openmatch_b200.dataset import InferenceDataset
+    rng = np.random.default_rng(0)
+    n, width = 53, 20
+    ids = rng.integers(1, 1000, (n, width)).astype(np.int32)
+    for r in range(n):
+        ids[r, rng.integers(3, width):] = 0
+    path = tmp_path / "corpus.npy"
+    np.save(path, ids)
+    (tmp_path / "corpus.ids.txt").write_text("\n".join("doc%d" % i for i in range(n)))
+    for p_max_len in (16, 20, 24):  # narrower than / equal to / wider than the stored width
+        d = DataArguments(corpus_path=str(path), p_max_len=p_max_len)
+        total = 0
+        for W in (1, 3):
+            for r in range(W):
+                ds = InferenceDataset.load(None, d, is_query=False, batch_size=8, num_processes=W, process_index=r)
+                per_row = list(ds)
+                blocks = list(ds.iter_batches())
+                names = [x for b in blocks for x in b[0]]
+                rows = np.concatenate([b[1] for b in blocks]) if blocks else np.zeros((0, p_max_len), np.int32)
+                assert names == [e["text_id"] for e in per_row]
+                assert rows.dtype == np.int32 and rows.shape == (len(per_row), p_max_len)
+                assert (rows == np.array([e["input_ids"] for e in per_row]).reshape(len(per_row), p_max_len)).all()
+                assert ds.num_local_rows() == len(per_row)
+                assert all(b[1].shape[0] <= 8 for b in blocks)
+                total += len(per_row) if W == 3 else 0
+        assert total == n

@@ -130,3 +130,41 @@ def test_training_forward_matches_reference_loss(small_bert, golden_dir):
     small_bert.zero_grad(set_to_none=True)
     model.eval()
     small_bert.cpu()
+
+
+def test_block_ingest_writes_index_rows_in_place(small_bert, tmp_path):
+    # PretokenizedDataset.iter_batches -> pinned staging -> encoder writing straight into reserve_rows: same embeddings,
+    # ids and row order as the per-example DataLoader path, and index.ntotal == len(doc_lookup)
+    from openmatch.arguments import DataArguments, ModelArguments
+    from openmatch.dataset import InferenceDataset
+    from openmatch.modeling import DRModelForInference
+    from openmatch.retriever import Retriever
+    rng = np.random.default_rng(1)
+    n, L = 75, 24
+    ids = rng.integers(5, 500, (n, L)).astype(np.int32)
+    for r in range(n):
+        ids[r, rng.integers(4, L):] = 0
+    np.save(tmp_path / "c.npy", ids)
+    (tmp_path / "c.ids.txt").write_text("\n".join("p%d" % i for i in range(n)))
+    dargs = DataArguments(corpus_path=str(tmp_path / "c.npy"), p_max_len=32)
+    margs = ModelArguments(model_name_or_path="unused")
+    model = DRModelForInference(lm_q=small_bert, lm_p=small_bert, model_args=margs)
+    assert model.rep_dim() == 128
+    out_a, out_b = tmp_path / "a", tmp_path / "b"
+    ds = InferenceDataset.load(None, dargs, is_query=False, batch_size=16)
+    fast = Retriever.build_all(model, ds, _args(out_a))
+    assert fast.index.ntotal == n == len(fast.doc_lookup) and fast.doc_lookup[:2] == ["p0", "p1"]
+
+    class PerExample(torch.utils.data.IterableDataset):  # hides iter_batches: forces the DataLoader + collator path
+        def __iter__(self):
+            return iter(InferenceDataset.load(None, dargs, is_query=False, batch_size=16))
+
+    slow = Retriever.build_all(DRModelForInference(lm_q=small_bert, lm_p=small_bert, model_args=margs), PerExample(),
+                               _args(out_b))
+    assert slow.doc_lookup == fast.doc_lookup
+    a, b = fast.index.master_rows().cpu(), slow.index.master_rows().cpu()
+    assert torch.equal(a, b), "block ingest and per-example ingest disagree"
+    with open(out_a / "embeddings.corpus.rank.0", "rb") as f:
+        enc, names = pickle.load(f)
+    assert enc.shape == (n, 128) and names == fast.doc_lookup and np.array_equal(enc, a.numpy())
+    small_bert.cpu()

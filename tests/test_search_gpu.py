@@ -289,8 +289,8 @@ def test_near_duplicate_cluster_is_exact(om):
     D, I = idx.search(q, k)
     assert idx.stat("uncertified") == q.shape[0]
     assert idx.stat("exact_queries") == q.shape[0], "near-duplicate queries must fall through to the exact scan"
-    _eps_check(q, x, D, I, k)
-    assert _recall(I, q, x, k) > 0.999
+    _eps_check(q, x, D, I, k, rel=2e-6)  # d = 128: fp32 summation noise is ~1e-6 |q||x|, the cluster's score spread 1e-4
+    assert _recall(I, q, x, k) > 0.99   # vs float64: only fp32 near-ties at the k-th rank may differ
     assert np.isin(I, dup).all(), "the top-k must lie inside the duplicate cluster"
     # the exact scan and the re-score share one summation order: exact_only reproduces the answer bit for bit
     idx.set_param("exact_only", 1)
@@ -316,7 +316,7 @@ def test_small_duplicate_cluster_resolved_by_wide_level(om):
     D, I = idx.search(q, k)
     assert idx.stat("uncertified") == q.shape[0]
     assert idx.stat("exact_queries") == 0 and idx.stat("uncertified_wide") == 0
-    _eps_check(q, x, D, I, k)
+    _eps_check(q, x, D, I, k, rel=2e-6)
     idx.set_param("exact_only", 1)
     De, Ie = idx.search(q, k)
     np.testing.assert_array_equal(Ie, I)
