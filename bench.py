@@ -75,39 +75,82 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / throttle reasons sampled every 100 ms while the timed region runs: NVML in-process (pynvml; a polling
+    `nvidia-smi -lms` child stalls CUDA launches for tens of ms per query on these boxes), nvidia-smi only as fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.stop, self.thread, self.how = [], None, gpu_index, False, None, None
 
     def __enter__(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+            def pump():
+                while not self.stop:
+                    try:
+                        r = int(get_reasons(h))
+                        self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(max_sm),
+                                          "%.1f" % (pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                                          "Active" if r & bits["hw_slowdown"] else "Not Active",
+                                          "Active" if r & bits["hw_thermal_slowdown"] else "Not Active",
+                                          "Active" if r & bits["sw_thermal_slowdown"] else "Not Active",
+                                          "Active" if r & bits["sw_power_cap"] else "Not Active"])
+                    except Exception:
+                        pass
+                    time.sleep(0.1)
+
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return self
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "500"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
         return self
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
+        elif self.thread:
+            self.thread.join(timeout=1.0)
 
     def summary(self):
         sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "via": self.how}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm),
+                "via": self.how}
 
 
 # ------------------------------------------------------------------------------------------------------------------

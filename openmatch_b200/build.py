@@ -56,10 +56,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB_PATH, objs):
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # link next to the target and rename: the library in the tree is always complete (it ships with repo snapshots)
+        tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+        cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

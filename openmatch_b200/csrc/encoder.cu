@@ -3,17 +3,25 @@
 // -> 'first' / 'mean' pooling (:145-150, src/openmatch/utils.py:233-235) -> bias-free LinearHead
 // (src/openmatch/modeling/linear.py:19,22-23) -> F.normalize (:153-154).
 //
-// Per layer (T = B*L tokens, H hidden, I = heads*64 attention width, F ffn):
-//   QKV    tcgen05 GEMM [T,H]x[3I,H]^T, epilogue: +bias -> bf16 Q|K [T,2I] and V transposed [I, T]
+// Per layer (T = B*L tokens, H hidden, I = heads*64 attention width, F ffn).  LayerNorm / RMSNorm never runs as a
+// kernel of its own: the residual stream is kept UN-normalised (s, fp32 + a bf16 copy) together with per-row (sum,
+// sum of squares); the normalisation is folded algebraically into the GEMM that consumes it,
+//        LN(s) W^T = rstd * (s Wf^T) + (W beta + b),   Wf = W diag(gamma) with every row centred (sum_i Wf[j, i] = 0,
+//        which makes the "- rstd * mean * rowsum" term vanish; RMSNorm has no mean, rows stay as they are),
+// and into the residual read of the GEMM that produces the next s:
+//   QKV    tcgen05 GEMM [T,H]x[3I,H]^T on bf16(s) and the folded weights; epilogue: rstd[row] * acc + folded bias
+//          -> bf16 Q|K [T,2I] and V transposed [I, T]
 //   ATTN   one CTA per (128-row tile, head): S = Q K^T (tcgen05, TMEM) -> masked softmax in registers
 //          (thread = query row) -> P (bf16, 128B-swizzled smem) -> O = P V (tcgen05) -> ctx bf16 [T,I]
-//   OPROJ  tcgen05 GEMM [T,I]x[H,I]^T, epilogue: +bias +residual -> fp32 residual stream (in place)
-//   NORM   LayerNorm (BERT) / RMSNorm (T5): fp32 statistics, writes fp32 stream + bf16 GEMM operand
-//   FFN1   tcgen05 GEMM [T,H]x[F,H]^T, epilogue: +bias, GELU(erf) / ReLU -> bf16 [T,F]
-//   FFN2   tcgen05 GEMM [T,F]x[H,F]^T, epilogue: +bias +residual -> fp32 stream (in place)
-// Activations feeding tensor cores are bf16; the residual stream, normalisation statistics, softmax,
-// pooling, head and L2-normalisation are fp32.
+//   OPROJ  tcgen05 GEMM [T,I]x[H,I]^T, epilogue (EpiResidNorm): s' = acc + bias + LN(s) (BERT) / + s (T5), written in
+//          place as fp32 (TMA load + TMA store of the residual tile) and as bf16, row statistics of s' accumulated
+//   FFN1   tcgen05 GEMM [T,H]x[F,H]^T on bf16(s') and folded weights; epilogue: rstd[row] * acc + folded bias, GELU(erf) /
+//          ReLU -> bf16 [T,F]
+//   FFN2   tcgen05 GEMM [T,F]x[H,F]^T, epilogue (EpiResidNorm) like OPROJ -> next layer's s
+// One norm kernel runs after the last layer (last_hidden_state for pooling).  Activations feeding tensor cores are
+// bf16; the residual stream, normalisation statistics, softmax, pooling, head and L2-normalisation are fp32.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -60,6 +68,37 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 }
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+// Normalisation of one row of the residual stream from its (sum, sum of squares): rstd and rstd * mean.
+// The statistics arrive as kStatParts partial (sum, sumsq) pairs per row — one per (column tile, epilogue column group)
+// of the GEMM that produced the row, summed here in a fixed order (deterministic, no atomics); unused slots hold zeros.
+// LayerNorm: var = E[x^2] - mean^2 (fp32; clamped at 0), RMSNorm: mean = 0.  stats == nullptr: identity (rstd 1, rm 0).
+constexpr int kStatParts = 8;
+struct RowNorm {
+  const float* stats;  // [T, kStatParts, 2] or nullptr
+  float inv_h, eps;
+  int rms;
+  __device__ __forceinline__ void get(int row, int M, float& rstd, float& rm) const {
+    rstd = 1.f;
+    rm = 0.f;
+    if (stats && row < M) {
+      const float4* p = reinterpret_cast<const float4*>(stats + static_cast<int64_t>(row) * (2 * kStatParts));
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < kStatParts / 2; ++j) {
+        const float4 t = __ldg(p + j);
+        sum += t.x;
+        sq += t.y;
+        sum += t.z;
+        sq += t.w;
+      }
+      const float mean = rms ? 0.f : sum * inv_h;
+      const float var = fmaxf(sq * inv_h - mean * mean, 0.f);
+      rstd = rsqrtf(var + eps);
+      rm = rstd * mean;
+    }
+  }
+};
 
 // Coalescing stage for bf16 epilogue outputs.  A thread owns one accumulator ROW, so a direct 16-byte store
 // per lane touches 32 different cache lines per warp instruction and the SM's load/store unit — not the tensor
@@ -127,23 +166,30 @@ struct StagedBf16 {
   }
 };
 
-// out bf16 [M, ldo] = act(acc + bias)
+// out bf16 [M, ldo] = act(rstd[row] * acc + bias[col])   (norm.stats == nullptr: rstd = 1, plain act(acc + bias)).
+// The mean term of a folded LayerNorm needs no work here: the folded weight rows are centred (fold_norm_kernel), so
+// sum_i s_i W''[j, i] already equals sum_i (s_i - mean) W'[j, i].
 template <int ACT>
 struct EpiBiasActBf16 {
   CUtensorMap tm_out;  // box {64 cols, 32 rows} over out, SWIZZLE_128B (TMA store)
   __nv_bfloat16* out;
   int64_t ldo;
-  const float* bias;  // nullable
+  const float* bias;  // nullable (folded bias W beta + b when the input is normalised)
   int M, N;
+  RowNorm norm;
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
   __host__ __device__ static constexpr int smem_bytes(int epi_warps) { return epi_warps * StagedBf16::kBytesPerWarp; }
   struct State {
     StagedBf16 stage;
+    float rstd, rm;
   };
   __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const { s.stage.bind(smem, epi_tid); }
   __device__ __forceinline__ void finish(State& s) const { s.stage.finish(); }
-  __device__ __forceinline__ void begin(State& s, int, int, int) const { s.stage.have = 0; }
+  __device__ __forceinline__ void begin(State& s, int row, int, int) const {
+    s.stage.have = 0;
+    norm.get(row, M, s.rstd, s.rm);
+  }
   __device__ __forceinline__ void end(State& s, int row) const { s.stage.flush_tail(out, ldo, row, M); }
   __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
     if (col0 >= N) return;  // warp-uniform; N is a multiple of 32 for every encoder GEMM (checked on the host)
@@ -154,9 +200,10 @@ struct EpiBiasActBf16 {
       const float4 t = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       bv[4 * j] = t.x, bv[4 * j + 1] = t.y, bv[4 * j + 2] = t.z, bv[4 * j + 3] = t.w;
     }
+    const float2 rs = splat2(s.rstd);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      float2 ab = add2(make_float2(v[i], v[i + 1]), make_float2(bv[i], bv[i + 1]));
+      float2 ab = fma2(rs, make_float2(v[i], v[i + 1]), make_float2(bv[i], bv[i + 1]));
       if (ACT == ACT_GELU) {
         ab = gelu_erf2(ab);
       } else if (ACT == ACT_RELU) {
@@ -178,21 +225,24 @@ struct EpiQKV {
   __nv_bfloat16* qk;
   __nv_bfloat16* vt;
   int64_t ldv;
-  const float* bias;  // nullable, [3I]
+  const float* bias;  // nullable, [3I] (folded: W beta + b)
   int M, I2;          // I2 = 2*I
   int valid_rows;     // tokens per attention tile (spt * L)
+  RowNorm norm;       // normalisation of the input rows, applied here (see the file header)
   static constexpr int kPasses = 1;
   static constexpr bool kPrefetch = false;
   __host__ __device__ static constexpr int smem_bytes(int epi_warps) { return epi_warps * StagedBf16::kBytesPerWarp; }
   struct State {
     int vcol;
     StagedBf16 stage;
+    float rstd, rm;
   };
   __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const { s.stage.bind(smem, epi_tid); }
   __device__ __forceinline__ void finish(State& s) const { s.stage.finish(); }
   __device__ __forceinline__ void begin(State& s, int row, int, int) const {
     s.vcol = (row / valid_rows) * 128 + row % valid_rows;
     s.stage.have = 0;
+    norm.get(row, M, s.rstd, s.rm);
   }
   __device__ __forceinline__ void end(State& s, int row) const { s.stage.flush_tail(qk, I2, row, M); }
   __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32]) const {
@@ -203,16 +253,165 @@ struct EpiQKV {
       const float4 t = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       bv[4 * j] = t.x, bv[4 * j + 1] = t.y, bv[4 * j + 2] = t.z, bv[4 * j + 3] = t.w;
     }
+    const float rstd = s.rstd;
     if (col0 < I2) {
       uint32_t packed[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) packed[i >> 1] = pack_bf16x2(v[i] + bv[i], v[i + 1] + bv[i + 1]);
+      for (int i = 0; i < 32; i += 2)
+        packed[i >> 1] = pack_bf16x2(fmaf(rstd, v[i], bv[i]), fmaf(rstd, v[i + 1], bv[i + 1]));
       s.stage.push(packed, &tm_qk, row, col0);
     } else if (row < M) {
       __nv_bfloat16* dst = vt + static_cast<int64_t>(col0 - I2) * ldv + s.vcol;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        dst[static_cast<int64_t>(i) * ldv] = __float2bfloat16(v[i] + bv[i]);  // lanes = consecutive tokens
+        dst[static_cast<int64_t>(i) * ldv] = __float2bfloat16(fmaf(rstd, v[i], bv[i]));  // lanes = consecutive tokens
+    }
+  }
+};
+
+// Residual epilogue of the O-proj and FFN2 GEMMs:   s'[m, n] = acc + bias[n] + R(s[m, n])
+//   R = LayerNorm of the residual stream with the producer's (gamma, beta) and the row's (mean, rstd)   (BERT, post-LN)
+//   R = identity                                                                                        (T5, pre-norm)
+// s lives in fp32 [T, H] and is updated IN PLACE; bf16(s') goes to xb (the next GEMM's A operand) and every (thread, tile)
+// writes its partial (sum, sum of squares) of s' into its own slot of stats_out for whoever normalises s' next.
+// A thread owns an accumulator ROW, so touching global memory directly would cost one cache line per lane and
+// instruction; instead each warp moves its 32-row x 32-column chunks through shared memory with TMA:
+//   TMA load  s[32 rows, 32 cols] fp32 -> 4 KB tile (SWIZZLE_128B; the first chunk of a tile is requested before the
+//             accumulator wait, the residual of the NEXT tile is pulled into L2 a tile ahead; one tile per warp: the
+//             shared memory a second one would take buys the mainloop its 4th ring stage, worth more — measured)
+//   in place  thread r rewrites row r of the tile (16-byte pieces XOR-ed with r & 7: conflict-free) and writes bf16(s')
+//             into a 2 KB tile (SWIZZLE_64B: 64-byte rows, also conflict-free)
+//   TMA store both tiles; rows >= M are clipped by the tensor maps.
+struct EpiResidNorm {
+  CUtensorMap tm_s;   // fp32 s [T, H], box {32 cols, 32 rows}, SWIZZLE_128B (load and store)
+  CUtensorMap tm_xb;  // bf16 xb [T, H], box {32 cols, 32 rows}, SWIZZLE_64B (store)
+  const float* bias;  // nullable [N]
+  RowNorm norm;       // statistics of s (norm.stats == nullptr: R = identity)
+  const float* gamma;  // [N] LayerNorm weight / bias applied to the residual (BERT); unused when norm.stats == nullptr
+  const float* beta;
+  float* stats_out;  // [T, kStatParts, 2]: slot n_blk * parts + column group <- this thread's (sum, sumsq) of s'
+  int parts;         // column groups per tile (epilogue warps / 4); (N / BN) * parts <= kStatParts
+  int M, N;
+  int bn;            // tile width (BN of the GEMM): geometry of the static tile schedule, for the L2 prefetch below
+  static constexpr int kPasses = 1;
+  static constexpr bool kPrefetch = true;
+  static constexpr bool kRolled = true;  // one copy of chunk() in the kernel (gemm.cuh)
+  static constexpr int kF32Tile = 4096, kBf16Tile = 2048, kPerWarp = kF32Tile + kBf16Tile;
+  static constexpr int kMaxN = 1024;     // per-column constants staged in shared memory: 2 * kMaxN floats
+  __host__ __device__ static constexpr int smem_bytes(int epi_warps) { return epi_warps * kPerWarp + 1024 + 2 * kMaxN * 4; }
+  struct State {
+    uint8_t* f32tile;   // [4096]
+    uint8_t* bf16tile;  // [2048]
+    uint64_t* bars;     // [1]
+    const float* gsm;   // [N] gamma of the residual's LayerNorm (1 when there is none)
+    const float* bsm;   // [N] bias + beta
+    uint32_t parity;    // phase parity of bars[0]
+    int slot;           // statistics slot of this (tile, column group)
+    int group;          // column group of this warp
+    float rstd, rm, rsum, rsq;
+  };
+  __device__ __forceinline__ void bind(State& s, uint8_t* smem, int epi_tid) const {
+    const int w = epi_tid >> 5, nw = blockDim.x / 32 - kGemmProducerThreads / 32;
+    s.f32tile = smem + w * kF32Tile;                        // 1024-byte aligned (swizzle atoms)
+    s.bf16tile = smem + nw * kF32Tile + w * kBf16Tile;       // 512-byte aligned is enough for SWIZZLE_64B
+    s.bars = reinterpret_cast<uint64_t*>(smem + nw * kPerWarp) + w;
+    s.parity = 0;
+    s.group = w >> 2;
+    if ((epi_tid & 31) == 0) {
+      mbar_init(&s.bars[0], 1);
+      fence_barrier_init();
+    }
+    // per-column constants, once per CTA: every lane of a chunk reads the same column's gamma / (bias + beta), so they
+    // come from shared memory as broadcasts instead of 24 dependent global loads per chunk and thread
+    float* gs = reinterpret_cast<float*>(smem + nw * kPerWarp + 1024);
+    float* bs = gs + kMaxN;
+    const bool ln = norm.stats != nullptr;
+    for (int c = epi_tid; c < N; c += nw * 32) {
+      gs[c] = ln ? gamma[c] : 1.f;
+      bs[c] = (bias ? bias[c] : 0.f) + (ln ? beta[c] : 0.f);
+    }
+    s.gsm = gs;
+    s.bsm = bs;
+    named_bar_sync(1, nw * 32);  // the epilogue warps only (the producer / MMA warps never join barrier 1)
+  }
+  __device__ __forceinline__ void finish(State&) const {
+    if ((threadIdx.x & 31) == 0) bulk_wait_group0();
+  }
+  __device__ __forceinline__ void begin(State& s, int row, int m_blk, int n_blk) const {
+    norm.get(row, M, s.rstd, s.rm);
+    s.rsum = 0.f;
+    s.rsq = 0.f;
+    s.slot = n_blk * parts + s.group;
+    // The residual of the tile this CTA processes NEXT (static schedule: tile + gridDim.x, n fastest) is pulled into L2
+    // now, a whole tile ahead: its TMA loads then cost an L2 hit instead of an exposed HBM round trip per chunk.
+    if ((threadIdx.x & 31) == 0) {
+      const int num_n = (N + bn - 1) / bn, num_m = (M + kBlockM - 1) / kBlockM;
+      const int next = m_blk * num_n + n_blk + static_cast<int>(gridDim.x);
+      if (next < num_m * num_n) {
+        const int nm = next / num_n, nn = next - nm * num_n;
+        const int row0 = row + (nm - m_blk) * kBlockM;  // lane 0's row = first row of the warp's slab
+        const int cols = bn / parts;                     // columns per column group
+#pragma unroll 1
+        for (int c = 0; c < cols; c += 32) tma_prefetch_l2_2d(&tm_s, nn * bn + s.group * cols + c, row0);
+      }
+    }
+  }
+  // request the residual of chunk [row0 .. row0+32) x [col0 .. col0+32) into tile `b` (lane 0; the tile's last TMA store
+  // must have finished READING it: the caller waits for that)
+  __device__ __forceinline__ void request(State& s, int row0, int col0) const {
+    bulk_wait_group_read0();  // the tile's last TMA store has finished reading it
+    mbar_arrive_expect_tx(&s.bars[0], kF32Tile);
+    tma_load_2d(s.f32tile, &tm_s, &s.bars[0], col0, row0);
+  }
+  __device__ __forceinline__ void prefetch(State& s, int row, int col0) const {
+    if (col0 >= N) return;  // warp-uniform
+    if ((threadIdx.x & 31) == 0) request(s, row, col0);  // lane 0's row = first row of the warp's 32-row slab
+  }
+  __device__ __forceinline__ void end(State& s, int row) const {
+    if (row < M)
+      *reinterpret_cast<float2*>(stats_out + (static_cast<int64_t>(row) * kStatParts + s.slot) * 2) = make_float2(s.rsum, s.rsq);
+  }
+  __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int next_col0) const {
+    if (col0 >= N) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    mbar_wait_warp(&s.bars[0], s.parity, 20);
+    s.parity ^= 1u;
+    uint8_t* mine = s.f32tile + lane * 128;
+    uint8_t* mineb = s.bf16tile + lane * 64;
+    // R = (s - mean) * rstd * gamma + beta = s * (rstd * gamma) + (beta - rstd * mean * gamma); without a LayerNorm on the
+    // residual (T5) gamma = 1, rstd = 1, mean = 0:  s' = acc + s * (rstd g) + ((bias + beta) - rstd mean g)
+    const float rstd = s.rstd, nrm = -s.rm;
+    const float4* gp = reinterpret_cast<const float4*>(s.gsm + col0);
+    const float4* bp = reinterpret_cast<const float4*>(s.bsm + col0);
+    float rsum = 0.f, rsq = 0.f;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      float4* slot = reinterpret_cast<float4*>(mine + ((p ^ (lane & 7)) << 4));
+      const float4 r = *slot;
+      const float4 g = gp[p], bb = bp[p];
+      float4 o;
+      o.x = fmaf(r.x, rstd * g.x, fmaf(nrm, g.x, bb.x)) + v[4 * p];
+      o.y = fmaf(r.y, rstd * g.y, fmaf(nrm, g.y, bb.y)) + v[4 * p + 1];
+      o.z = fmaf(r.z, rstd * g.z, fmaf(nrm, g.z, bb.z)) + v[4 * p + 2];
+      o.w = fmaf(r.w, rstd * g.w, fmaf(nrm, g.w, bb.w)) + v[4 * p + 3];
+      *slot = o;
+      rsum += (o.x + o.y) + (o.z + o.w);
+      rsq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, rsq))));
+      // bf16 tile: 64-byte rows, 16-byte piece (p >> 1) XOR-ed with (row >> 1) & 3 (SWIZZLE_64B)
+      uint2* hb = reinterpret_cast<uint2*>(mineb + ((((p >> 1) ^ ((lane >> 1) & 3)) << 4) | ((p & 1) << 3)));
+      *hb = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+    if (row < M) {  // rows beyond M hold zero-filled residuals + garbage-free accumulators, but must not count
+      s.rsum += rsum;
+      s.rsq += rsq;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tm_s, s.f32tile, col0, row);
+      tma_store_2d(&tm_xb, s.bf16tile, col0, row);
+      bulk_commit_group();
+      if (next_col0 >= 0 && next_col0 < N) request(s, row, next_col0);  // waits for the stores above to release the tile
     }
   }
 };
@@ -304,11 +503,41 @@ __global__ void __launch_bounds__(128) norm_kernel(float* h, const __nv_bfloat16
                out_bf16 ? out_bf16 + static_cast<int64_t>(row) * H : nullptr);
 }
 
-// BERT embeddings: LayerNorm(word[id] + type[tt] + pos[l])  (modeling_bert.py:53-112)
+// Row statistics of a freshly embedded row: slot 0 of the row's kStatParts partials holds (sum, sum of squares), the
+// other slots zeros (the GEMM epilogues that normalise the row sum all slots, see RowNorm).
+__device__ __forceinline__ void store_row_stats(const float4 (&v)[kMaxVec], int nvec, int lane, float* stats_row) {
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) {
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      q = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, q))));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane < kStatParts) reinterpret_cast<float2*>(stats_row)[lane] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ void raw_store(const float4 (&v)[kMaxVec], int nvec, int lane, float* out_f32,
+                                          __nv_bfloat16* out_bf16) {
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) {
+      const int c = (j * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(out_f32 + c) = v[j];
+      *reinterpret_cast<uint2*>(out_bf16 + c) = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+    }
+}
+
+// BERT embeddings (modeling_bert.py:53-112): s = word[id] + type[tt] + pos[l], UN-normalised (fp32 + bf16) with its row
+// statistics; the embedding LayerNorm is applied by the first layer's QKV / O-proj epilogues like every other LayerNorm.
 __global__ void __launch_bounds__(128) bert_embed_kernel(const int64_t* ids, const int64_t* tts, const float* word,
-                                                         const float* type, const float* pos, const float* gamma,
-                                                         const float* beta, float eps, int T, int L, int H, int vocab,
-                                                         int type_vocab, float* out_f32, __nv_bfloat16* out_bf16) {
+                                                         const float* type, const float* pos, int T, int L, int H, int vocab,
+                                                         int type_vocab, float* out_f32, __nv_bfloat16* out_bf16,
+                                                         float* stats) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
   const int nvec = H >> 7;
@@ -327,20 +556,52 @@ __global__ void __launch_bounds__(128) bert_embed_kernel(const int64_t* ids, con
       const float4 p = *reinterpret_cast<const float4*>(pos + static_cast<int64_t>(l) * H + c);
       v[j] = make_float4((a.x + b.x) + p.x, (a.y + b.y) + p.y, (a.z + b.z) + p.z, (a.w + b.w) + p.w);
     }
-  norm_row<false>(v, nvec, H, eps);
-  affine_store(v, nvec, lane, gamma, beta, out_f32 + static_cast<int64_t>(row) * H,
-               out_bf16 + static_cast<int64_t>(row) * H);
+  raw_store(v, nvec, lane, out_f32 + static_cast<int64_t>(row) * H, out_bf16 + static_cast<int64_t>(row) * H);
+  store_row_stats(v, nvec, lane, stats + static_cast<int64_t>(row) * (2 * kStatParts));
 }
 
-// T5: h = embed_tokens[id] (no position embedding, no scaling; modeling_t5.py:682,734)
-__global__ void t5_embed_kernel(const int64_t* ids, const float* emb, int T, int H, int vocab, float* out) {
+// T5: h = embed_tokens[id] (no position embedding, no scaling; modeling_t5.py:682,734), fp32 + bf16 + row statistics
+__global__ void __launch_bounds__(128) t5_embed_kernel(const int64_t* ids, const float* emb, int T, int H, int vocab,
+                                                       float* out_f32, __nv_bfloat16* out_bf16, float* stats) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T) return;
+  const int nvec = H >> 7;
   int64_t id = ids[row];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  for (int c = lane * 4; c < H; c += 128)
-    *reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * H + c) =
-        *reinterpret_cast<const float4*>(emb + id * H + c);
+  float4 v[kMaxVec];
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec) v[j] = *reinterpret_cast<const float4*>(emb + id * H + (j * 32 + lane) * 4);
+  raw_store(v, nvec, lane, out_f32 + static_cast<int64_t>(row) * H, out_bf16 + static_cast<int64_t>(row) * H);
+  store_row_stats(v, nvec, lane, stats + static_cast<int64_t>(row) * (2 * kStatParts));
+}
+
+// Weight folding (once, at om_encoder_finalize):  Wf[j, i] = bf16(W[j, i] * gamma[i] - centre * mean_i(W[j, i] * gamma[i]))
+// and bfold[j] = b[j] + sum_i W[j, i] * beta[i] (fp32, un-centred W).  With centred rows (LayerNorm) the mean term of the
+// folded normalisation vanishes identically:  sum_i s_i Wf[j, i] = sum_i (s_i - mean(s)) W[j, i] gamma[i]  (up to the bf16
+// rounding of Wf, ~1e-3 of a weight: below the bf16 rounding of the GEMM's output).  RMSNorm (T5): centre = 0, beta = none.
+// One warp per output row j.
+__global__ void __launch_bounds__(256) fold_norm_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ bias,
+                                                        int N, int K, int centre, __nv_bfloat16* __restrict__ Wf,
+                                                        float* bfold) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= N) return;
+  const float* w = W + static_cast<int64_t>(j) * K;
+  float c = 0.f, b = 0.f;
+  for (int i = lane; i < K; i += 32) {
+    const float wi = w[i];
+    c = fmaf(wi, gamma[i], c);
+    if (beta) b = fmaf(wi, beta[i], b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const float shift = centre ? c / static_cast<float>(K) : 0.f;
+  for (int i = lane; i < K; i += 32) Wf[static_cast<int64_t>(j) * K + i] = __float2bfloat16(fmaf(w[i], gamma[i], -shift));
+  if (lane == 0 && bfold) bfold[j] = b + (bias ? bias[j] : 0.f);
 }
 
 __global__ void keymask_kernel(const int64_t* attn_mask, float* kmask, int T) {
@@ -821,6 +1082,10 @@ struct LayerW {
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;          // BERT only
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;  // BERT: post-attn / post-ffn LN
                                                                                  // T5  : pre-attn / pre-ffn RMS (g only)
+  // normalisation folded into the consuming GEMM (om_encoder_finalize): wqkv / w1 hold W diag(gamma) in bf16 (rows
+  // centred for LayerNorm), b*_fold = W beta + b (BERT); fp32 staging freed after folding
+  float *wqkv_f32 = nullptr, *w1_f32 = nullptr;
+  float *bqkv_fold = nullptr, *b1_fold = nullptr;
 };
 
 struct om_encoder {
@@ -840,7 +1105,8 @@ struct om_encoder {
   // workspace
   int Tmax = 0, Tld = 0;
   float *h = nullptr, *kmask = nullptr, *pooled = nullptr, *headed = nullptr;
-  __nv_bfloat16 *xb = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *inter = nullptr, *obuf = nullptr;
+  __nv_bfloat16 *xb = nullptr, *qk = nullptr, *vt = nullptr, *ctx = nullptr, *inter = nullptr;
+  float* stats[2] = {nullptr, nullptr};  // [Tmax, kStatParts, 2] row statistics of the residual stream (ping-pong)
   std::vector<void*> allocs;
 };
 
@@ -952,8 +1218,15 @@ int om_encoder_create(const om_encoder_desc* desc, om_encoder** out) {
     A(&w.w2, (size_t)H * F);
     A(&w.ln1_g, H);
     A(&w.ln2_g, H);
+    if (rc == 0 && (cudaMalloc(&w.wqkv_f32, (size_t)3 * I * H * 4) != cudaSuccess ||
+                    cudaMalloc(&w.w1_f32, (size_t)F * H * 4) != cudaSuccess)) {
+      cudaGetLastError();
+      rc = fail(OM_ENOMEM, "om_encoder_create: out of device memory (weight staging)");
+    }
     char buf[160];
     if (d.arch == OM_ARCH_BERT) {
+      A(&w.bqkv_fold, (size_t)3 * I);
+      A(&w.b1_fold, F);
       A(&w.bqkv, (size_t)3 * I);
       A(&w.bo, H);
       A(&w.b1, F);
@@ -993,14 +1266,18 @@ int om_encoder_create(const om_encoder_desc* desc, om_encoder** out) {
   A(&e->vt, (size_t)I * e->Tld);
   A(&e->ctx, T * I);
   A(&e->inter, T * F);
-  A(&e->obuf, T * H);
+  A(&e->stats[0], T * 2 * kStatParts);
+  A(&e->stats[1], T * 2 * kStatParts);
   A(&e->pooled, T * H);  // at most Tmax sequences (L >= 1)
   A(&e->headed, (size_t)e->Tmax * std::max(d.head_out, 1));
   if (rc != 0) {
     om_encoder_destroy(e);
     return rc;
   }
-  if (cudaMemset(e->vt, 0, (size_t)I * e->Tld * 2) != cudaSuccess) {
+  // statistics slots a GEMM configuration never writes must read as zero (see RowNorm)
+  if (cudaMemset(e->stats[0], 0, T * 2 * kStatParts * 4) != cudaSuccess ||
+      cudaMemset(e->stats[1], 0, T * 2 * kStatParts * 4) != cudaSuccess ||
+      cudaMemset(e->vt, 0, (size_t)I * e->Tld * 2) != cudaSuccess) {
     om_encoder_destroy(e);
     return fail(OM_ECUDA, "workspace memset failed");
   }
@@ -1011,6 +1288,10 @@ int om_encoder_create(const om_encoder_desc* desc, om_encoder** out) {
 void om_encoder_destroy(om_encoder* e) {
   if (!e) return;
   for (void* p : e->allocs) cudaFree(p);
+  for (LayerW& w : e->layers) {
+    cudaFree(w.wqkv_f32);
+    cudaFree(w.w1_f32);
+  }
   delete e;
 }
 
@@ -1056,7 +1337,8 @@ int om_encoder_set_weight(om_encoder* e, const char* name_c, const void* data, o
       if (slot >= 0) {
         if (is_w) {
           if (!shape_is(shape, ndim, I, H)) return bad_shape(name_c);
-          OM_TRY(upload(data, kind, (size_t)I * H, nullptr, w.wqkv + (size_t)slot * I * H));
+          if (!w.wqkv_f32) return fail(OM_ESTATE, "om_encoder_set_weight after om_encoder_finalize");
+          OM_TRY(upload(data, kind, (size_t)I * H, w.wqkv_f32 + (size_t)slot * I * H, nullptr));
         } else {
           if (!shape_is(shape, ndim, I)) return bad_shape(name_c);
           OM_TRY(upload(data, kind, I, w.bqkv + (size_t)slot * I, nullptr));
@@ -1076,7 +1358,8 @@ int om_encoder_set_weight(om_encoder* e, const char* name_c, const void* data, o
       } else if (mod == "intermediate.dense") {
         if (is_w) {
           if (!shape_is(shape, ndim, F, H)) return bad_shape(name_c);
-          OM_TRY(upload(data, kind, (size_t)F * H, nullptr, w.w1));
+          if (!w.w1_f32) return fail(OM_ESTATE, "om_encoder_set_weight after om_encoder_finalize");
+          OM_TRY(upload(data, kind, (size_t)F * H, w.w1_f32, nullptr));
         } else {
           if (!shape_is(shape, ndim, F)) return bad_shape(name_c);
           OM_TRY(upload(data, kind, F, w.b1, nullptr));
@@ -1117,7 +1400,8 @@ int om_encoder_set_weight(om_encoder* e, const char* name_c, const void* data, o
                  rest == "layer.0.SelfAttention.v.weight") {
         const int slot = rest[22] == 'q' ? 0 : rest[22] == 'k' ? 1 : 2;
         if (!shape_is(shape, ndim, I, H)) return bad_shape(name_c);
-        OM_TRY(upload(data, kind, (size_t)I * H, nullptr, w.wqkv + (size_t)slot * I * H));
+        if (!w.wqkv_f32) return fail(OM_ESTATE, "om_encoder_set_weight after om_encoder_finalize");
+        OM_TRY(upload(data, kind, (size_t)I * H, w.wqkv_f32 + (size_t)slot * I * H, nullptr));
       } else if (rest == "layer.0.SelfAttention.o.weight") {
         if (!shape_is(shape, ndim, H, I)) return bad_shape(name_c);
         OM_TRY(upload(data, kind, (size_t)H * I, nullptr, w.wo));
@@ -1126,7 +1410,8 @@ int om_encoder_set_weight(om_encoder* e, const char* name_c, const void* data, o
         OM_TRY(upload(data, kind, H, rest[6] == '0' ? w.ln1_g : w.ln2_g, nullptr));
       } else if (rest == "layer.1.DenseReluDense.wi.weight") {
         if (!shape_is(shape, ndim, F, H)) return bad_shape(name_c);
-        OM_TRY(upload(data, kind, (size_t)F * H, nullptr, w.w1));
+        if (!w.w1_f32) return fail(OM_ESTATE, "om_encoder_set_weight after om_encoder_finalize");
+        OM_TRY(upload(data, kind, (size_t)F * H, w.w1_f32, nullptr));
       } else if (rest == "layer.1.DenseReluDense.wo.weight") {
         if (!shape_is(shape, ndim, H, F)) return bad_shape(name_c);
         OM_TRY(upload(data, kind, (size_t)H * F, nullptr, w.w2));
@@ -1165,6 +1450,30 @@ int om_encoder_finalize(om_encoder* e) {
                          cudaMemcpyHostToDevice));
     }
   }
+  // fold every normalisation into the GEMM that consumes it (file header): BERT layer l's QKV takes the LayerNorm that
+  // produced its input (embeddings.LayerNorm for l = 0, else layer l-1's output.LayerNorm) and W1 takes
+  // attention.output.LayerNorm; T5 block l's QKV / wi take its own pre-norm RMS weights (no beta, no mean term).
+  {
+    const bool bert = e->d.arch == OM_ARCH_BERT;
+    const int H = e->d.hidden, I = e->I, F = e->d.ffn;
+    for (int li = 0; li < e->d.layers; ++li) {
+      LayerW& w = e->layers[li];
+      if (!w.wqkv_f32 || !w.w1_f32) return fail(OM_ESTATE, "om_encoder_finalize called twice");
+      const float* g_in = bert ? (li == 0 ? e->emb_g : e->layers[li - 1].ln2_g) : w.ln1_g;
+      const float* b_in = bert ? (li == 0 ? e->emb_b : e->layers[li - 1].ln2_b) : nullptr;
+      fold_norm_kernel<<<(3 * I + 7) / 8, 256>>>(w.wqkv_f32, g_in, b_in, bert ? w.bqkv : nullptr, 3 * I, H, bert ? 1 : 0,
+                                                 w.wqkv, w.bqkv_fold);
+      fold_norm_kernel<<<(F + 7) / 8, 256>>>(w.w1_f32, bert ? w.ln1_g : w.ln2_g, bert ? w.ln1_b : nullptr,
+                                             bert ? w.b1 : nullptr, F, H, bert ? 1 : 0, w.w1, w.b1_fold);
+    }
+    OM_CUDA(cudaGetLastError());
+    OM_CUDA(cudaDeviceSynchronize());
+    for (LayerW& w : e->layers) {
+      cudaFree(w.wqkv_f32);
+      cudaFree(w.w1_f32);
+      w.wqkv_f32 = w.w1_f32 = nullptr;
+    }
+  }
   static bool attr = false;
   if (!attr) {
     OM_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -1198,12 +1507,15 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
   const bool bert = d.arch == OM_ARCH_BERT;
   const int rows4 = (T + 3) / 4;
 
+  NvtxRange nvtx("om.encode");
   keymask_kernel<<<(T + 255) / 256, 256, 0, st>>>(attention_mask, e->kmask, T);
+  // the residual stream s lives in e->h (fp32, un-normalised) with a bf16 copy in e->xb and row statistics in
+  // e->stats[0] (input of a layer: from the embedding or the previous FFN2) / e->stats[1] (after the attention block)
   if (bert)
-    bert_embed_kernel<<<rows4, 128, 0, st>>>(input_ids, token_type_ids, e->word, e->type, e->pos, e->emb_g, e->emb_b,
-                                             d.ln_eps, T, L, H, d.vocab, std::max(d.type_vocab, 1), e->h, e->xb);
+    bert_embed_kernel<<<rows4, 128, 0, st>>>(input_ids, token_type_ids, e->word, e->type, e->pos, T, L, H, d.vocab,
+                                             std::max(d.type_vocab, 1), e->h, e->xb, e->stats[0]);
   else
-    t5_embed_kernel<<<rows4, 128, 0, st>>>(input_ids, e->word, T, H, d.vocab, e->h);
+    t5_embed_kernel<<<rows4, 128, 0, st>>>(input_ids, e->word, T, H, d.vocab, e->h, e->xb, e->stats[0]);
   OM_CUDA(cudaGetLastError());
 
   // attention geometry
@@ -1224,22 +1536,35 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       make_tmap_bf16_2d(&tmVt, e->vt, (uint64_t)n_tiles * 128, (uint64_t)I, (uint64_t)e->Tld * 2, 64, 64) != 0)
     return fail(OM_ECUDA, "om_encode: tensor map creation failed");
 
-  // TMA-store tensor maps of the three bf16 GEMM outputs (box = 64 columns x 32 rows = one epilogue warp's pair)
-  CUtensorMap tmQKout, tmObuf, tmInter;
+  // TMA-store tensor maps of the bf16 GEMM outputs (box = 64 columns x 32 rows = one epilogue warp's chunk pair) and the
+  // residual stream's maps (fp32 load + store, bf16 store; box = 32 columns x 32 rows = one chunk)
+  CUtensorMap tmQKout, tmInter, tmS, tmXb;
   if (make_tmap_bf16_2d(&tmQKout, e->qk, (uint64_t)2 * I, (uint64_t)T, (uint64_t)2 * I * 2, 64, 32) != 0 ||
-      make_tmap_bf16_2d(&tmObuf, e->obuf, (uint64_t)H, (uint64_t)T, (uint64_t)H * 2, 64, 32) != 0 ||
-      make_tmap_bf16_2d(&tmInter, e->inter, (uint64_t)F, (uint64_t)T, (uint64_t)F * 2, 64, 32) != 0)
+      make_tmap_bf16_2d(&tmInter, e->inter, (uint64_t)F, (uint64_t)T, (uint64_t)F * 2, 64, 32) != 0 ||
+      make_tmap_2d(&tmS, e->h, 4, (uint64_t)H, (uint64_t)T, (uint64_t)H * 4, 32, 32, 128) != 0 ||
+      make_tmap_2d(&tmXb, e->xb, 2, (uint64_t)H, (uint64_t)T, (uint64_t)H * 2, 32, 32, 64) != 0)
     return fail(OM_ECUDA, "om_encode: output tensor map creation failed");
-  // `pending` = bf16 output of the last O-proj / FFN2 GEMM that has not been added to the residual stream yet
-  const __nv_bfloat16* pending = nullptr;
+  const float inv_h = 1.0f / static_cast<float>(H);
+  const int rms = bert ? 0 : 1;
+  const RowNorm normA{e->stats[0], inv_h, d.ln_eps, rms}, normB{e->stats[1], inv_h, d.ln_eps, rms};
+  const RowNorm ident{nullptr, inv_h, d.ln_eps, rms};
+  // residual GEMMs (N = H): 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
+  // waves of full tiles); 8 epilogue warps = 2 column groups per tile -> (H / BN) * 2 <= kStatParts statistics slots
+  auto resid_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* W, EpiResidNorm epi) -> cudaError_t {
+    if (H % 192 == 0) return launch_gemm<192, 4, false, 8>(A, K, W, K, T, H, K, epi, sms, st);
+    epi.parts = 1;  // 256-wide tiles: a 4-stage ring leaves room for 4 epilogue warps (one column group)
+    return launch_gemm<256, 4, false, 4>(A, K, W, K, T, H, K, epi, sms, st);
+  };
+  if ((H % 192 == 0 ? H / 192 : (H + 255) / 256) * 2 > kStatParts)
+    return fail(OM_EINVAL, "om_encode: hidden=%d needs more statistics slots than kStatParts", H);
   for (int li = 0; li < d.layers; ++li) {
     const LayerW& w = e->layers[li];
-    if (!bert) {  // T5 pre-norm: h += pending; x = RMSNorm(h)
-      norm_kernel<true, true><<<rows4, 128, 0, st>>>(e->h, pending, w.ln1_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
-      pending = nullptr;
-    }
+    NvtxRange nvtx_layer("om.encode.layer");
+    // LayerNorm that produced this layer's input (BERT; applied on the fly wherever the input is consumed)
+    const float* g_in = bert ? (li == 0 ? e->emb_g : e->layers[li - 1].ln2_g) : nullptr;
+    const float* b_in = bert ? (li == 0 ? e->emb_b : e->layers[li - 1].ln2_b) : nullptr;
     {
-      EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv : nullptr, T, 2 * I, ap.Tvalid_rows};
+      EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv_fold : nullptr, T, 2 * I, ap.Tvalid_rows, normA};
       cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
     }
@@ -1249,45 +1574,43 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
     OM_CUDA(cudaGetLastError());
     {
-      // N = H: 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
-      // waves of full tiles): less wave-quantisation loss on 148 SMs.  Store-only epilogue (bf16).
-      EpiBiasActBf16<ACT_NONE> epi{tmObuf, e->obuf, H, bert ? w.bo : nullptr, T, H};
-      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st)
-                                       : launch_gemm<256, 4, false, 8>(e->ctx, I, w.wo, I, T, H, I, epi, sms, st);
+      // s <- ctx Wo^T + bo + LN_in(s) (BERT) / + s (T5); statistics of the new s -> stats[1]
+      EpiResidNorm epi{tmS, tmXb, bert ? w.bo : nullptr, bert ? normA : ident, g_in, b_in, e->stats[1], 2, T, H,
+                       H % 192 == 0 ? 192 : 256};
+      cudaError_t err = resid_gemm(e->ctx, I, w.wo, epi);
       if (err != cudaSuccess) return fail(OM_ECUDA, "O-proj GEMM launch failed: %s", cudaGetErrorString(err));
     }
-    if (bert)  // h = LN(h + o)
-      norm_kernel<false, false><<<rows4, 128, 0, st>>>(e->h, e->obuf, w.ln1_g, w.ln1_b, d.ln_eps, T, H, e->h, e->xb);
-    else  // h += o; x = RMSNorm(h)
-      norm_kernel<true, true><<<rows4, 128, 0, st>>>(e->h, e->obuf, w.ln2_g, nullptr, d.ln_eps, T, H, nullptr, e->xb);
     {
       cudaError_t err;
       if (bert) {
-        EpiBiasActBf16<ACT_GELU> epi{tmInter, e->inter, F, w.b1, T, F};
+        EpiBiasActBf16<ACT_GELU> epi{tmInter, e->inter, F, w.b1_fold, T, F, normB};
         err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
       } else {
-        EpiBiasActBf16<ACT_RELU> epi{tmInter, e->inter, F, nullptr, T, F};
+        EpiBiasActBf16<ACT_RELU> epi{tmInter, e->inter, F, nullptr, T, F, normB};
         err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
       }
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN1 GEMM launch failed: %s", cudaGetErrorString(err));
     }
     {
-      EpiBiasActBf16<ACT_NONE> epi{tmObuf, e->obuf, H, bert ? w.b2 : nullptr, T, H};
-      cudaError_t err = (H % 192 == 0) ? launch_gemm<192, 4, false, 12>(e->inter, F, w.w2, F, T, H, F, epi, sms, st)
-                                       : launch_gemm<256, 4, false, 8>(e->inter, F, w.w2, F, T, H, F, epi, sms, st);
+      // s <- inter W2^T + b2 + LN_attn(s) (BERT) / + s (T5); statistics -> stats[0] (the next layer's input)
+      EpiResidNorm epi{tmS, tmXb, bert ? w.b2 : nullptr, bert ? normB : ident, w.ln1_g, w.ln1_b, e->stats[0], 2, T, H,
+                       H % 192 == 0 ? 192 : 256};
+      cudaError_t err = resid_gemm(e->inter, F, w.w2, epi);
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN2 GEMM launch failed: %s", cudaGetErrorString(err));
     }
-    if (bert)
-      norm_kernel<false, false><<<rows4, 128, 0, st>>>(e->h, e->obuf, w.ln2_g, w.ln2_b, d.ln_eps, T, H, e->h, e->xb);
-    else
-      pending = e->obuf;  // added by the next layer's first norm (or the final norm)
-    OM_CUDA(cudaGetLastError());
   }
-  if (!bert)  // final_layer_norm over h + pending
-    norm_kernel<true, false><<<rows4, 128, 0, st>>>(e->h, pending, e->final_g, nullptr, d.ln_eps, T, H, e->h, nullptr);
+  // the one normalisation that runs as a kernel: last_hidden_state = LN_out(s) (BERT: last layer's output.LayerNorm,
+  // T5: final_layer_norm), in place in e->h, for pooling and the optional out_hidden copy
+  if (bert)
+    norm_kernel<false, false><<<rows4, 128, 0, st>>>(e->h, nullptr, e->layers[d.layers - 1].ln2_g,
+                                                     e->layers[d.layers - 1].ln2_b, d.ln_eps, T, H, e->h, nullptr);
+  else
+    norm_kernel<true, false><<<rows4, 128, 0, st>>>(e->h, nullptr, e->final_g, nullptr, d.ln_eps, T, H, e->h, nullptr);
+  OM_CUDA(cudaGetLastError());
   if (out_hidden)
     OM_CUDA(cudaMemcpyAsync(out_hidden, e->h, static_cast<size_t>(T) * H * 4, cudaMemcpyDeviceToDevice, st));
 
+  NvtxRange nvtx_pool("om.encode.pool_head_normalize");
   pool_kernel<<<B, 256, 0, st>>>(e->h, attention_mask, L, H, d.pooling == OM_POOL_MEAN ? 1 : 0, e->pooled);
   const float* reps = e->pooled;
   if (d.has_head) {

@@ -16,6 +16,8 @@
 // Pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue); static persistent
 // tile schedule (tile = blockIdx.x + i * gridDim.x).
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -57,6 +59,12 @@ struct GemmCfg {
 //        row) and a second sweep with pass 1 follow (TMEM re-reads are cheap; the search filter uses this as
 //        its overflow path when a thread finds more survivors than its stash holds)
 // Rows >= M and columns >= N contain zeros (TMA out-of-bounds fill) and must be masked by the functor.
+
+// Epi::kRolled (optional, default false): see the epilogue loop
+template <class Epi, class = void>
+struct epi_rolled : std::false_type {};
+template <class Epi>
+struct epi_rolled<Epi, std::void_t<decltype(Epi::kRolled)>> : std::bool_constant<Epi::kRolled> {};
 
 template <int BN, int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, bool F16 = false>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
@@ -257,6 +265,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else
             epi.chunk(st, row, n_blk * BN + c * 32, v);
         };
+        if constexpr (epi_rolled<Epi>::value) {
+          // heavy epilogues (hundreds of instructions per chunk): ONE copy of the chunk code, chunks processed in a rolled
+          // loop; the exposed TMEM-load latency (~100 cycles per chunk) is noise next to the chunk's own work, while
+          // three inlined copies (double-buffered loads + tail) made the kernel 4.7 K instructions and fetch-bound
+          uint32_t ra[32];
+#pragma unroll 1
+          for (int c = c0; c < c0 + kChunks; ++c) {
+            tmem_ld_32x32b_x32(taddr + c * 32, ra);
+            tmem_ld_wait();
+            run(ra, c, c + 1 < c0 + kChunks);
+          }
+          continue;
+        }
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32(taddr + c0 * 32, ra);
         if constexpr (kChunks == 1) {

@@ -365,6 +365,7 @@ extern "C" int om_contrastive_loss_fwd_bwd(const void* Q, const void* P, om_dtyp
   if (!target && np < nq) return fail(OM_EINVAL, "loss: default target needs np >= nq");
   const int sms = device_sm_count();
   if (sms < 0) return sms;
+  NvtxRange nvtx("om.loss");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LossWs& ws = g_loss_ws;
   const int dpad = (int)round_up(d, 8), nqp = (int)round_up(nq, 8), npp = (int)round_up(np, 8);

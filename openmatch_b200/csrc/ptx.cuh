@@ -161,6 +161,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
       "l"(policy)
       : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // TMA store: shared (128B-swizzled box) -> global, tracked by the thread's bulk async-group.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

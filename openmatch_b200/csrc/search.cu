@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) certify_kernel(const float* __restrict__ 
                                                       const int* __restrict__ ghist, int kp_target,
                                                       const float* __restrict__ hn, const float* __restrict__ en,
                                                       const float* __restrict__ gstats, int d, int nq, int q_base,
-                                                      int* flag_list, int* nflag) {
+                                                      int* flags, int* nflag) {
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= nq) return;
   float tau;
@@ -494,7 +494,37 @@ __global__ void __launch_bounds__(256) certify_kernel(const float* __restrict__ 
   const float E = 1.001f * (a * exmax + b * xmax + static_cast<float>(d + 16) * 2.384185791015625e-07f * (a + b) * (xmax + exmax));
   const bool full = I[static_cast<size_t>(q) * k + (k - 1)] >= 0;  // fewer than k results: every row was a candidate
   const bool ok = !full || (D[static_cast<size_t>(q) * k + (k - 1)] - tau > E);
-  if (!ok && lane == 0) flag_list[atomicAdd(nflag, 1)] = q_base + q;
+  // flags, not an appended list: the order of the uncertified queries must be the same on every rank of a sharded search
+  if (lane == 0) {
+    flags[q_base + q] = ok ? 0 : 1;
+    if (!ok) atomicAdd(nflag, 1);
+  }
+}
+
+// list[0 .. count) = ascending indices i with flags[i] != 0 (one block; chunked block-wide scan)
+__global__ void __launch_bounds__(1024) compact_flags_kernel(const int* __restrict__ flags, int n, int* __restrict__ list) {
+  __shared__ int warp_sums[32];
+  __shared__ int base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const bool f = i < n && flags[i] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_sums[warp] = __popc(b);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_sums[w];
+    if (f) list[off + __popc(b & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_sums[w];
+      base += t;
+    }
+    __syncthreads();
+  }
 }
 
 // EXACT fp32 scan on the CUDA cores (the certificate's last resort and the "exact_only" test mode): one warp per
@@ -882,6 +912,8 @@ struct Timed {
   cudaStream_t st;
   bool on;
   Timed(om_index* ix_, cudaStream_t st_, int kind) : ix(ix_), st(st_), on(ix_->profile != 0) {
+    static const char* nvtx_names[4] = {"om.search.scan", "om.search.select", "om.search.rescore", "om.search.exchange_certify"};
+    nvtxRangePushA(nvtx_names[kind & 3]);
     if (!on) return;
     if (ix->ev_used + 2 > ix->ev.size()) {
       cudaEvent_t a, b;
@@ -897,6 +929,7 @@ struct Timed {
     cudaEventRecord(ix->ev[ix->ev_used], st);
   }
   ~Timed() {
+    nvtxRangePop();
     if (!on) return;
     cudaEventRecord(ix->ev[ix->ev_used + 1], st);
     ix->ev_used += 2;
@@ -1147,13 +1180,14 @@ int exchange_chunk(om_index* ix, om_comm* comm, const Level& L, int q0, int nqc,
 
 // Runs one level over all its queries and returns the number of uncertified ones (their indices in flag_list).
 // One host synchronisation at the end (status word); list overflow / a too-narrow exchange redo the level.
-int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int64_t id_offset, int* flag_list,
-              int* nflag_out, cudaStream_t st) {
+int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int64_t id_offset, int* flags,
+              int* flag_list, int* nflag_out, cudaStream_t st) {
   const int sms = device_sm_count();
   if (sms < 0) return sms;
+  NvtxRange nvtx(L.mode == 1 ? "om.search.level_exact" : (L.kp_target >= kMaxCandidates ? "om.search.level_wide" : "om.search.level0"));
   const bool sharded = comm && comm->world > 1;
   bool safe = ix->force_safe != 0, wide = false;
-  const bool certify = ix->certify && L.mode == 0 && flag_list != nullptr && !ix->stage_scores;
+  const bool certify = ix->certify && L.mode == 0 && flags != nullptr && !ix->stage_scores;
   for (int attempt = 0; attempt < 4; ++attempt) {
     OM_CUDA(cudaMemsetAsync(L.status, 0, 32, st));
     for (int q0 = 0; q0 < L.nq; q0 += kQueryChunk) {
@@ -1169,7 +1203,7 @@ int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int
         certify_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(dD + static_cast<size_t>(q0) * L.k, dI + static_cast<size_t>(q0) * L.k,
                                                       L.k, L.thr, sharded ? L.range : nullptr, sharded ? L.hist : nullptr,
                                                       L.kp_target, L.hn + q0, L.en + q0,
-                                                      sharded ? L.range + 2 * nqc : ix->gstats, ix->d, nqc, q0, flag_list,
+                                                      sharded ? L.range + 2 * nqc : ix->gstats, ix->d, nqc, q0, flags,
                                                       L.status + 2);
         OM_CUDA(cudaGetLastError());
         ix->st_launches += 1;
@@ -1193,6 +1227,11 @@ int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int
       continue;
     }
     *nflag_out = certify ? ix->h_status[2] : 0;
+    if (*nflag_out > 0) {  // ascending list of the uncertified queries (identical on every rank)
+      compact_flags_kernel<<<1, 1024, 0, st>>>(flags, L.nq, flag_list);
+      OM_CUDA(cudaGetLastError());
+      ix->st_launches += 1;
+    }
     return 0;
   }
   return fail(OM_EFAULT, "search level did not converge (bug)");
@@ -1202,6 +1241,7 @@ int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int
 // level 2 (still uncertified: exact fp32 scan).  comm == nullptr / world 1: single shard.
 int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, int nq, int k, float* D, int64_t* I,
                 om_memkind out_kind, int64_t id_offset, cudaStream_t st) {
+  NvtxRange nvtx("om.search");
   const int d = ix->d;
   const int world = comm ? comm->world : 1;
   ix->plan.valid = false;  // the level workspace is about to be reused
@@ -1219,7 +1259,8 @@ int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, i
   const size_t o_q = carve(q_kind == OM_HOST ? static_cast<size_t>(nq) * d * 4 : 0);
   const size_t o_D = carve(out_kind == OM_HOST ? static_cast<size_t>(nq) * k * 4 : 0);
   const size_t o_I = carve(out_kind == OM_HOST ? static_cast<size_t>(nq) * k * 8 : 0);
-  const size_t o_flag = carve(static_cast<size_t>(nq) * 4);   // level-0 uncertified queries (indices)
+  const size_t o_flags = carve(static_cast<size_t>(nq) * 4);  // per-query 0 / 1 written by the certificate of a level
+  const size_t o_flag = carve(static_cast<size_t>(nq) * 4);   // level-0 uncertified queries (ascending indices)
   const size_t o_sub = carve(static_cast<size_t>(nq) * 4);    // uncertified within an escalation sub-batch
   const size_t o_flag2 = carve(static_cast<size_t>(nq) * 4);  // ... composed back to indices into the full set
   OM_TRY(ix->ows.reserve(off));
@@ -1231,6 +1272,7 @@ int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, i
   }
   float* dD = out_kind == OM_HOST ? reinterpret_cast<float*>(ob + o_D) : D;
   int64_t* dI = out_kind == OM_HOST ? reinterpret_cast<int64_t*>(ob + o_I) : I;
+  int* flags = reinterpret_cast<int*>(ob + o_flags);
   int* flag_list = reinterpret_cast<int*>(ob + o_flag);
   int* sub_flags = reinterpret_cast<int*>(ob + o_sub);
   int* flag_list2 = reinterpret_cast<int*>(ob + o_flag2);
@@ -1241,7 +1283,7 @@ int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, i
   if (!ix->exact_only) {
     Level L;
     OM_TRY(level_prepare(ix, L, qf, nq, k, kp0, 0, world, st));
-    OM_TRY(run_level(ix, comm, L, dD, dI, id_offset, flag_list, &nf, st));
+    OM_TRY(run_level(ix, comm, L, dD, dI, id_offset, flags, flag_list, &nf, st));
     ix->st_flagged = nf;
   }
   // Escalation: the queries listed in `list` (indices into the full set; nullptr = all of them) are gathered into a
@@ -1250,7 +1292,7 @@ int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, i
     Level Ls;
     if (!list) {
       OM_TRY(level_prepare(ix, Ls, qf, n_sub, k, kp_target, mode, world, st));
-      return run_level(ix, comm, Ls, dD, dI, id_offset, sub_flags, nf_out, st);
+      return run_level(ix, comm, Ls, dD, dI, id_offset, flags, sub_flags, nf_out, st);
     }
     size_t so = 0;
     auto scarve = [&](size_t bytes) {
@@ -1268,7 +1310,7 @@ int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, i
     gather_rows_kernel<<<grid_for(static_cast<int64_t>(n_sub) * d, 256), 256, 0, st>>>(qf, list, n_sub, d, qsub);
     OM_CUDA(cudaGetLastError());
     OM_TRY(level_prepare(ix, Ls, qsub, n_sub, k, kp_target, mode, world, st));
-    OM_TRY(run_level(ix, comm, Ls, Ds, Is, id_offset, sub_flags, nf_out, st));
+    OM_TRY(run_level(ix, comm, Ls, Ds, Is, id_offset, flags, sub_flags, nf_out, st));
     scatter_results_kernel<<<grid_for(static_cast<int64_t>(n_sub) * k, 256), 256, 0, st>>>(Ds, Is, list, n_sub, k, dD, dI);
     OM_CUDA(cudaGetLastError());
     ix->st_launches += 2;

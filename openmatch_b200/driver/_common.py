@@ -28,5 +28,11 @@ def load_tokenizer(model_args, **kw):
 
 def load_config(model_args):
     from transformers import AutoConfig
-    return AutoConfig.from_pretrained(model_args.config_name or model_args.model_name_or_path, num_labels=1,
-                                      cache_dir=model_args.cache_dir)
+    path = model_args.config_name or model_args.model_name_or_path
+    # An UNTIED OpenMatch checkpoint keeps its HF configs under query_model/ and passage_model/ (DRModel.save,
+    # dense_retrieval_model.py:230-245) and has no config.json at the root, which the reference's drivers trip over
+    # (AutoConfig.from_pretrained(root), build_index.py:24-28) unless --config_name is given: resolve it here.
+    if os.path.isdir(path) and not os.path.exists(os.path.join(path, "config.json")) and \
+            os.path.exists(os.path.join(path, "passage_model", "config.json")):
+        path = os.path.join(path, "passage_model")
+    return AutoConfig.from_pretrained(path, num_labels=1, cache_dir=model_args.cache_dir)

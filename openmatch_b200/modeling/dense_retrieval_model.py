@@ -116,8 +116,22 @@ class DRModel(nn.Module):
             return None, None
         decoder_path = "T5" in type(model).__name__ and not (self.model_args is not None and self.model_args.encoder_only)
         if decoder_path:
-            raise NotImplementedError("encoder-decoder T5 pooling (decoder_input_ids) is outside the B200 hot path; "
-                                      "use --encoder_only")
+            # The reference's default T5 mode (:137-141): the full encoder-decoder with a single zero decoder token, reps =
+            # decoder last_hidden_state[:, 0].  The decoder is outside the CUDA encoder (GTR / --encoder_only is the hot
+            # path), so this mode runs the HF module on the GPU — for training and for inference alike.
+            if not getattr(self, "_warned_decoder_path", False):
+                logger.warning("encoder-decoder T5 pooling runs the HuggingFace module (not the sm_100a encoder); "
+                               "use --encoder_only for the accelerated path")
+                self._warned_decoder_path = True
+            dec = torch.zeros((items["input_ids"].shape[0], 1), dtype=torch.long, device=items["input_ids"].device)
+            out = model(**{k: v for k, v in items.items()}, decoder_input_ids=dec, return_dict=True)
+            hidden = out.last_hidden_state
+            reps = hidden[:, 0, :]
+            if head is not None:
+                reps = head(reps)
+            if self.normalize:
+                reps = F.normalize(reps, dim=1)
+            return hidden, reps
         if self.feature != "last_hidden_state":
             raise NotImplementedError("only feature='last_hidden_state' is supported")
         input_ids = items["input_ids"]
@@ -161,6 +175,9 @@ class DRModel(nn.Module):
         intermediate ``[B, d]`` tensor and no copy.  Same arithmetic as ``encode`` (:133-155)."""
         model, head = (self.lm_q, self.head_q) if is_query else (self.lm_p, self.head_p)
         input_ids = items["input_ids"]
+        if "T5" in type(model).__name__ and not (self.model_args is not None and self.model_args.encoder_only):
+            out.copy_(self.encode(items, model, head, need_hidden=False)[1])  # encoder-decoder pooling: HF module
+            return out
         if not input_ids.is_cuda:
             raise RuntimeError("openmatch_b200 encodes on a CUDA device only (no CPU path): move the batch to GPU")
         enc = self._cuda_encoder(model, head)

@@ -118,3 +118,28 @@ def test_flat_index_semantics():
     assert (I3 == I2).all()
     idx.reset()
     assert idx.ntotal == 0
+
+
+def test_t5_encoder_decoder_pooling_matches_the_reference(golden_dir):
+    # the reference's default T5 mode (encoder_only=False, dense_retrieval_model.py:137-141): reps of DRModel.encode
+    # (HF module path, CPU is fine here) against the reference's own run on the same weights
+    import torch
+    from transformers import T5Config, T5Model
+
+    from openmatch_b200.arguments import ModelArguments
+    from openmatch_b200.modeling import DRModelForInference
+    z = np.load(os.path.join(golden_dir, "t5dec_small.npz"))
+    cfg = T5Config(vocab_size=120, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_decoder_layers=2, num_heads=4,
+                   feed_forward_proj="relu", dropout_rate=0.0)
+    lm = T5Model(cfg).eval()
+    lm.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    batch = {"input_ids": torch.from_numpy(z["ids"]), "attention_mask": torch.from_numpy(z["mask"])}
+    for normalize in (False, True):
+        model = DRModelForInference(lm_q=lm, lm_p=lm, tied=True, pooling="first", normalize=normalize,
+                                    model_args=ModelArguments(model_name_or_path="unused", encoder_only=False))
+        hidden, reps = model.encode_passage(batch)
+        assert hidden.shape == (5, 1, 32)
+        np.testing.assert_allclose(reps.numpy(), z["reps_norm%d" % int(normalize)], rtol=1e-5, atol=1e-6)
+        out = torch.empty(5, 32)
+        model.encode_into(batch, out)
+        np.testing.assert_allclose(out.numpy(), z["reps_norm%d" % int(normalize)], rtol=1e-5, atol=1e-6)

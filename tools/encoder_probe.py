@@ -1,30 +1,28 @@
-"""Scratch probe (not part of the product): encoder throughput on the GPU, synthetic bert-base / t5-base."""
+"""Scratch probe (not part of the product): encoder throughput on the GPU, synthetic bert-base / t5-base / bert-large.
+  python tools/encoder_probe.py [bert|t5|large] [B] [L] [iters]"""
+import os
 import sys
 
 import torch
 
-sys.path.insert(0, "tests")
-from test_encoder_gpu import _rand_bert_sd, _rand_t5_sd  # noqa: E402
-
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from openmatch_b200 import synthetic  # noqa: E402
 from openmatch_b200.encoder import CudaEncoder  # noqa: E402
 
 arch = sys.argv[1] if len(sys.argv) > 1 else "bert"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-gen = torch.Generator().manual_seed(0)
-H, F, layers, vocab = 768, 3072, 12, 30522
-if arch == "bert":
-    sd = _rand_bert_sd(gen, layers, H, F, vocab, 512)
-    spec = dict(arch="bert", layers=layers, hidden=H, heads=12, ffn=F, vocab=vocab, max_pos=512, type_vocab=2, ln_eps=1e-12)
-    enc = CudaEncoder(spec, sd, pooling="first", max_batch_tokens=B * L)
+if arch == "t5":
+    spec = dict(synthetic.T5_BASE)
+    enc = CudaEncoder(spec, synthetic.t5_state_dict(spec, seed=0), head_weight=torch.randn(768, 768) * 0.03, pooling="mean",
+                      normalize=True, max_batch_tokens=B * L)
 else:
-    sd = _rand_t5_sd(gen, layers, H, 12, F, 32128)
-    spec = dict(arch="t5", layers=layers, hidden=H, heads=12, ffn=F, vocab=32128, ln_eps=1e-6)
-    enc = CudaEncoder(spec, sd, head_weight=torch.randn(768, 768) * 0.03, pooling="mean", normalize=True, max_batch_tokens=B * L)
-ids = torch.randint(1000, 30000, (B, L), device="cuda")
-mask = torch.ones(B, L, dtype=torch.long, device="cuda")
-out = torch.empty(B, 768, device="cuda")
+    spec = dict(synthetic.BERT_LARGE if arch == "large" else synthetic.BERT_BASE)
+    enc = CudaEncoder(spec, synthetic.bert_state_dict(spec, seed=0), pooling="first", max_batch_tokens=B * L)
+H, layers = spec["hidden"], spec["layers"]
+ids, mask = synthetic.token_batch(B, L, spec["vocab"], seed=1, bert=arch != "t5", device="cuda")
+out = torch.empty(B, enc.rep_dim, device="cuda")
 for _ in range(3):
     enc.encode(ids, mask, out=out)
 torch.cuda.synchronize()
