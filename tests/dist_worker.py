@@ -104,16 +104,18 @@ report.append("near-duplicates exact")
 del one
 
 # ---- 4. skewed shards: every relevant row lives on the last rank -> fixed-width prefix too narrow -> wide exchange ----
-n, d, nq, k = 30000, 64, 9, 200
+n, d, nq, k = 30000, 64, 9, 1000  # k large enough that the fixed exchange width (1.5 kp / W + 64) is below k
 x = rng.integers(-3, 4, (n, d)).astype(np.float32)
 q = rng.integers(1, 4, (nq, d)).astype(np.float32)
-hot = n - 2000
-x[hot:] = rng.integers(2, 4, (2000, d)).astype(np.float32)  # all positive: dominate every all-positive query
+hot = n - 3000
+x[hot:] = rng.integers(2, 4, (3000, d)).astype(np.float32)  # all positive: dominate every all-positive query
 idx = sharded(x, np.linspace(0, n, world + 1).astype(int))
 D, I = idx.search(q, k)
 D0, I0 = oracle.flat_ip_search(q, x, k)
 assert (I == I0).all() and (D == D0).all()
-assert (I >= hot).all() and idx.local.stat("wide_exchanges") >= 1
+assert (I >= hot).all()
+assert idx.local.stat("wide_exchanges") >= 1, "stats: wide %d uncertified %d exact %d" % (
+    idx.local.stat("wide_exchanges"), idx.local.stat("uncertified"), idx.local.stat("exact_queries"))
 report.append("skewed shards -> wide exchange")
 
 # ---- 5. Retriever.from_embeddings with more files than ranks + _search_sharded ----
