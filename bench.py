@@ -80,10 +80,13 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, enabled=True):
         self.rows, self.proc, self.gpu, self.stop, self.thread, self.how = [], None, gpu_index, False, None, None
+        self.enabled = enabled  # rank 0 only: concurrent NVML pollers on every rank stalled a step by ~100 ms at N = 2
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -96,15 +99,14 @@ class ClockSampler:
                 while not self.stop:
                     try:
                         r = int(get_reasons(h))
-                        self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(max_sm),
-                                          "%.1f" % (pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                        self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(max_sm), "0",
                                           "Active" if r & bits["hw_slowdown"] else "Not Active",
                                           "Active" if r & bits["hw_thermal_slowdown"] else "Not Active",
                                           "Active" if r & bits["sw_thermal_slowdown"] else "Not Active",
                                           "Active" if r & bits["sw_power_cap"] else "Not Active"])
                     except Exception:
                         pass
-                    time.sleep(0.1)
+                    time.sleep(0.2)
 
             self.thread = threading.Thread(target=pump, daemon=True)
             self.thread.start()
@@ -332,7 +334,7 @@ def main():
         value_step()
         step_wall.append((time.perf_counter() - t0) * 1e3)  # host wall per step (diagnostic; every step ends synchronised)
 
-    with ClockSampler(local_rank) as clocks:  # started before the warm-up: nvidia-smi's start-up lands outside the timed steps
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clocks:  # started before the warm-up: nvidia-smi's start-up lands outside the timed steps
         for _ in range(args.warmup):
             search_step(q_dev)
         total_ms = timed(value_step_timed, args.steps, 0)

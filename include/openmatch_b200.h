@@ -118,9 +118,11 @@ int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int
 /* Row-sharded search with the exchange inside the library — replaces faiss.index_cpu_to_gpu_multiple(shard=True) +
  * IndexShards (src/openmatch/retriever/dense_retriever.py:43-58).  One process per GPU; every rank holds a contiguous
  * row shard and calls om_index_search_sharded with the same queries and its own id_offset; every rank receives the
- * same global (D, I).  All collectives (NCCL over NVLink: MAX all-reduce of the per-query score range, SUM all-reduce
- * of a 256-bin histogram, one packed all-gather of a fixed-width prefix of the per-shard lists) are issued on `stream`
- * between the kernels, with a single host synchronisation at the end; exactness is certified as in om_index_search.
+ * same global (D, I).  Each shard keeps a candidate list sized for its share of the answer (1.5 (k + slack) / world + 64
+ * rows), re-scores it in fp32 and ships it whole together with the list's stage-score floor and the shard's error-norm
+ * maxima in ONE packed NCCL all-gather per query chunk (issued on `stream` between the kernels, single host
+ * synchronisation at the end of a level); every rank merges the lists and runs the exactness certificate of
+ * om_index_search with tau = the largest floor.  Skewed shards fail the certificate and are answered by the wider levels.
  *   om_comm_unique_id : rank 0 obtains 128 opaque bytes (ncclGetUniqueId) and ships them to the other ranks
  *                       (e.g. torch.distributed.broadcast_object_list)
  *   om_comm_init      : collective over the `world` ranks (ncclCommInitRank) on the current device
@@ -163,7 +165,7 @@ int om_index_set_param(om_index* idx, const char* name, int64_t value);
 /* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity),
  * "launches" (kernels launched), "uncertified" (queries the first level could not prove exact),
  * "uncertified_wide" (still unproven with 4096 candidates), "exact_queries" (answered by the exact fp32 scan),
- * "wide_exchanges" (sharded levels redone at full exchange width), and with "profile" on: "scan_ns", "select_ns",
+ * and with "profile" on: "scan_ns", "select_ns",
  * "finalize_ns", "other_ns" (device time summed over the launches of each kind; other = exchange + merge + certify). */
 int64_t om_index_get_stat(const om_index* idx, const char* name);
 void om_index_destroy(om_index* idx);

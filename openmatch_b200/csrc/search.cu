@@ -466,34 +466,30 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* Dp, const int64
 //   |B - stage|      <= d * 2^-22 * ||q_h|| * ||x_h||            (fp32 accumulation of exact products in the tensor
 //                       core: d adds, each off by at most 2^-23 of the running magnitude if the hardware truncates
 //                       instead of rounding; x2 head-room.  tests/test_search_gpu.py measures the real value.)
-// with the corpus norms replaced by their maxima over the index (kept by rows_to_f16_kernel).  tau is the kp-th
-// stage score of the list (single shard) or the lower edge of the agreed histogram bin (sharded search).
+// with the corpus norms replaced by their maxima over the index (kept by rows_to_f16_kernel; sharded search: over all
+// shards).  tau is the kp-th stage score of the candidate list — sharded search: the largest of the shards' floors.
 // A NaN anywhere makes the comparison false: the query is flagged and answered by the exact path.
 __global__ void __launch_bounds__(256) certify_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int k,
-                                                      const float* __restrict__ thr, const float* __restrict__ range,
-                                                      const int* __restrict__ ghist, int kp_target,
-                                                      const float* __restrict__ hn, const float* __restrict__ en,
-                                                      const float* __restrict__ gstats, int d, int nq, int q_base,
-                                                      int* flags, int* nflag) {
+                                                      const float* __restrict__ floors, int64_t floor_stride, int nparts,
+                                                      const float* __restrict__ gstats, int64_t stats_stride,
+                                                      const float* __restrict__ hn, const float* __restrict__ en, int d,
+                                                      int nq, int q_base, int* flags, int* nflag) {
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= nq) return;
-  float tau;
-  if (range) {
-    const FloorBins fb = FloorBins::make(range[q], range[nq + q]);
-    const int minbin = ghist ? warp_min_bin(ghist + static_cast<size_t>(q) * kFloorBins, kp_target, lane) : 0;
-    tau = fb.lo;
-    if (minbin > 0 && fb.scale > 0.f) {
-      const float t = fb.lo + static_cast<float>(minbin) / fb.scale;
-      tau = t + (fabsf(t) + fabsf(fb.lo)) * 2e-6f;  // bin() rounds: a pruned score may sit a few ulps above the edge
-    }
-  } else {
-    tau = thr[q];
+  // tau: no row outside the re-scored candidate lists has a stage score above the largest per-shard floor (kp-th stage
+  // score of the shard's list; -inf when the shard's list holds every row of the shard); error-norm maxima likewise
+  float tau = __int_as_float(0xff800000), xmax = 0.f, exmax = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    tau = fmaxf(tau, floors[p * floor_stride + q]);
+    const float a = gstats[p * stats_stride], b = gstats[p * stats_stride + 1];
+    xmax = (a > xmax || a != a) ? a : xmax;  // NaN sticks: the comparison below then fails
+    exmax = (b > exmax || b != b) ? b : exmax;
   }
-  const float xmax = gstats[0], exmax = gstats[1];
   const float a = hn[q], b = en[q];
   const float E = 1.001f * (a * exmax + b * xmax + static_cast<float>(d + 16) * 2.384185791015625e-07f * (a + b) * (xmax + exmax));
-  const bool full = I[static_cast<size_t>(q) * k + (k - 1)] >= 0;  // fewer than k results: every row was a candidate
-  const bool ok = !full || (D[static_cast<size_t>(q) * k + (k - 1)] - tau > E);
+  // tau = -inf: every list holds every row of its shard, nothing was left out.  Otherwise k results are needed to compare.
+  const bool full = I[static_cast<size_t>(q) * k + (k - 1)] >= 0;
+  const bool ok = !(tau > __int_as_float(0xff800000)) ? true : (full && D[static_cast<size_t>(q) * k + (k - 1)] - tau > E);
   // flags, not an appended list: the order of the uncertified queries must be the same on every rank of a sharded search
   if (lane == 0) {
     flags[q_base + q] = ok ? 0 : 1;
@@ -694,9 +690,7 @@ struct Level {
   unsigned long long* cand = nullptr;
   int* count = nullptr;
   float* thr = nullptr;
-  int* status = nullptr;  // [0] list overflow, [1] exchange prefix too narrow, [2] uncertified queries
-  float* range = nullptr;
-  int* hist = nullptr;
+  int* status = nullptr;  // [0] list overflow, [2] uncertified queries
   uint8_t *send = nullptr, *recv = nullptr;
 };
 
@@ -959,6 +953,21 @@ int once_attrs() {
   return 0;
 }
 
+// Packed per-shard block of the sharded exchange for nqc queries shipping kc entries each:
+//   [D f32 nqc x kc | I i64 nqc x kc | floor f32 nqc (kp-th stage score of the shard's list) | error-norm maxima f32 x 2]
+struct ExchangeBlock {
+  size_t off_i, off_floor, off_stats, bytes;
+};
+inline ExchangeBlock exchange_block(size_t nqc, size_t kc) {
+  ExchangeBlock b;
+  b.off_i = round_up(nqc * kc * 4, 256);
+  b.off_floor = b.off_i + round_up(nqc * kc * 8, 256);
+  b.off_stats = b.off_floor + round_up(nqc * 4, 256);
+  b.bytes = b.off_stats + 256;
+  return b;
+}
+inline size_t exchange_block_bytes(size_t nqc, size_t kc) { return exchange_block(nqc, kc).bytes; }
+
 // sizes the candidate lists of a level, carves the level workspace and converts the queries
 int level_prepare(om_index* ix, Level& L, const float* qf, int nq, int k, int kp_target, int mode, int world,
                   cudaStream_t st) {
@@ -973,6 +982,12 @@ int level_prepare(om_index* ix, Level& L, const float* qf, int nq, int k, int kp
   L.mode = mode;
   L.world = world;
   L.kp_target = std::min(std::max(kp_target, k), kMaxCandidates);
+  // Row-sharded search: the global top-(k + slack) draws ~(k + slack) / W rows from every shard, so each shard keeps a
+  // list of 1.5x that + 64 instead of k + slack: scan survivors, select and re-score work all shrink W-fold and the whole
+  // list is shipped (no agreement phase).  A shard that holds more of the answer than its list (skewed shards) shows up
+  // as a high floor: the certificate fails and the query is escalated to the 4096-wide level, which keeps full lists.
+  if (world > 1 && mode == 0 && L.kp_target < kMaxCandidates)
+    L.kp_target = static_cast<int>(std::min<int64_t>(L.kp_target, round_up((3 * static_cast<int64_t>(L.kp_target)) / (2 * world) + 64, 32)));
   L.kp = static_cast<int>(std::min<int64_t>(L.kp_target, std::max<int64_t>(ix->n, 1)));
   // Expected list length after a round that multiplies the rows seen by g is ~g kp (kp kept + ~(g-1) kp new
   // survivors); 25 % + 512 entries of head-room cover its spread for exchangeable row order.
@@ -982,9 +997,7 @@ int level_prepare(om_index* ix, Level& L, const float* qf, int nq, int k, int kp
     if (L.C <= 16384 || L.growth == 2) break;
   }
   if (L.C > 16384) return fail(OM_EINVAL, "om_index_search: candidate list of %d entries exceeds 16384; lower k", L.C);
-  // sharded exchange: every shard ships a fixed-width prefix (expected kp / world rows + the agreed bin's share);
-  // a longer list raises status[1] and the level is redone at full width
-  L.kc = world > 1 ? static_cast<int>(std::min<int64_t>(k, round_up((3 * static_cast<int64_t>(L.kp_target)) / (2 * world) + 64, 32))) : k;
+  L.kc = std::min(k, L.kp_target);  // entries a shard ships per query (it cannot contribute more than k)
   L.nqc_max = std::min(nq, kQueryChunk);
   ix->st_capacity = L.C;
   size_t off = 0;
@@ -997,11 +1010,9 @@ int level_prepare(om_index* ix, Level& L, const float* qf, int nq, int k, int kp
   const size_t o_qh = carve(static_cast<size_t>(nq) * dpad * 2), o_hn = carve(static_cast<size_t>(nq) * 4),
                o_en = carve(static_cast<size_t>(nq) * 4), o_cand = carve(nqc * L.C * 8), o_count = carve(nqc * 4),
                o_thr = carve(nqc * 4), o_status = carve(256);
-  size_t o_range = 0, o_hist = 0, o_send = 0, o_recv = 0;
+  size_t o_send = 0, o_recv = 0;
   if (world > 1) {
-    const size_t blk = round_up(nqc * k * 4, 256) + round_up(nqc * k * 8, 256);
-    o_range = carve((2 * nqc + 2) * 4);
-    o_hist = carve(nqc * kFloorBins * 4);
+    const size_t blk = exchange_block_bytes(nqc, L.kc);
     o_send = carve(blk);
     o_recv = carve(blk * world);
   }
@@ -1014,8 +1025,6 @@ int level_prepare(om_index* ix, Level& L, const float* qf, int nq, int k, int kp
   L.count = reinterpret_cast<int*>(base + o_count);
   L.thr = reinterpret_cast<float*>(base + o_thr);
   L.status = reinterpret_cast<int*>(base + o_status);
-  L.range = world > 1 ? reinterpret_cast<float*>(base + o_range) : nullptr;
-  L.hist = world > 1 ? reinterpret_cast<int*>(base + o_hist) : nullptr;
   L.send = world > 1 ? base + o_send : nullptr;
   L.recv = world > 1 ? base + o_recv : nullptr;
   if (mode == 0) {
@@ -1146,47 +1155,38 @@ int merge_parts(const float* Dp, const int64_t* Ip, int64_t stride_d, int64_t st
   return rc;
 }
 
-// Exchange of one query chunk of a row-sharded level: the shards agree on a per-query score floor (MAX-reduced
-// (floor, best) range, SUM-reduced histogram), re-score only the candidates in or above the bin that holds the
-// global kp-th stage score, all-gather a fixed-width prefix of the per-shard lists and merge on every rank.
-int exchange_chunk(om_index* ix, om_comm* comm, const Level& L, int q0, int nqc, int kc, float* dD, int64_t* dI,
-                   int64_t id_offset, cudaStream_t st) {
+// Exchange of one query chunk of a row-sharded level: every shard re-scores its (shard-sized) candidate list in fp32 and
+// ships it whole — sorted scores, global ids, the list's stage-score floor and the shard's error-norm maxima — in ONE
+// packed all-gather; every rank then merges the W lists.  (The certificate is run by the caller on the merged result.)
+int exchange_chunk(om_index* ix, om_comm* comm, const Level& L, int q0, int nqc, float* dD, int64_t* dI, int64_t id_offset,
+                   cudaStream_t st) {
   NcclApi& nc = nccl_api();
   const int W = comm->world;
+  const ExchangeBlock b = exchange_block(nqc, L.kc);
+  OM_TRY(finalize_chunk(ix, L, q0, nqc, reinterpret_cast<float*>(L.send), reinterpret_cast<int64_t*>(L.send + b.off_i), L.kc,
+                        id_offset, nullptr, nullptr, nullptr, nullptr, st));
   {
     Timed t(ix, st, 3);
-    local_range_kernel<<<nqc, 256, 0, st>>>(L.cand, L.count, L.thr, L.C, nqc, ix->n >= L.kp_target ? 1 : 0, L.range,
-                                            ix->gstats);
-    OM_CUDA(cudaGetLastError());
-    OM_NCCL(nc.AllReduce(L.range, L.range, static_cast<size_t>(2 * nqc + 2), kNcclFloat32, kNcclMax, comm->nccl, st));
-    floor_hist_kernel<<<nqc, 256, 0, st>>>(L.cand, L.count, L.C, L.range, nqc, L.hist);
-    OM_CUDA(cudaGetLastError());
-    OM_NCCL(nc.AllReduce(L.hist, L.hist, static_cast<size_t>(nqc) * kFloorBins, kNcclInt32, kNcclSum, comm->nccl, st));
-  }
-  const size_t off_i = round_up(static_cast<size_t>(nqc) * kc * 4, 256);
-  const size_t blk = off_i + round_up(static_cast<size_t>(nqc) * kc * 8, 256);
-  OM_TRY(finalize_chunk(ix, L, q0, nqc, reinterpret_cast<float*>(L.send), reinterpret_cast<int64_t*>(L.send + off_i), kc,
-                        id_offset, L.range, L.hist, nullptr, kc < L.k ? L.status + 1 : nullptr, st));
-  {
-    Timed t(ix, st, 3);
-    OM_NCCL(nc.AllGather(L.send, L.recv, blk, kNcclInt8, comm->nccl, st));
-    OM_TRY(merge_parts(reinterpret_cast<const float*>(L.recv), reinterpret_cast<const int64_t*>(L.recv + off_i),
-                       static_cast<int64_t>(blk / 4), static_cast<int64_t>(blk / 8), W, nqc, kc, L.k,
+    OM_CUDA(cudaMemcpyAsync(L.send + b.off_floor, L.thr, static_cast<size_t>(nqc) * 4, cudaMemcpyDeviceToDevice, st));
+    OM_CUDA(cudaMemcpyAsync(L.send + b.off_stats, ix->gstats, 8, cudaMemcpyDeviceToDevice, st));
+    OM_NCCL(nc.AllGather(L.send, L.recv, b.bytes, kNcclInt8, comm->nccl, st));
+    OM_TRY(merge_parts(reinterpret_cast<const float*>(L.recv), reinterpret_cast<const int64_t*>(L.recv + b.off_i),
+                       static_cast<int64_t>(b.bytes / 4), static_cast<int64_t>(b.bytes / 8), W, nqc, L.kc, L.k,
                        dD + static_cast<size_t>(q0) * L.k, dI + static_cast<size_t>(q0) * L.k, st));
   }
-  ix->st_launches += 3;
+  ix->st_launches += 2;
   return 0;
 }
 
 // Runs one level over all its queries and returns the number of uncertified ones (their indices in flag_list).
-// One host synchronisation at the end (status word); list overflow / a too-narrow exchange redo the level.
+// One host synchronisation at the end (status word); a list overflow redoes the level with the safe schedule.
 int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int64_t id_offset, int* flags,
               int* flag_list, int* nflag_out, cudaStream_t st) {
   const int sms = device_sm_count();
   if (sms < 0) return sms;
   NvtxRange nvtx(L.mode == 1 ? "om.search.level_exact" : (L.kp_target >= kMaxCandidates ? "om.search.level_wide" : "om.search.level0"));
   const bool sharded = comm && comm->world > 1;
-  bool safe = ix->force_safe != 0, wide = false;
+  bool safe = ix->force_safe != 0;
   const bool certify = ix->certify && L.mode == 0 && flags != nullptr && !ix->stage_scores;
   for (int attempt = 0; attempt < 4; ++attempt) {
     OM_CUDA(cudaMemsetAsync(L.status, 0, 32, st));
@@ -1194,23 +1194,25 @@ int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int
       const int nqc = std::min(kQueryChunk, L.nq - q0);
       OM_TRY(sweep_chunk(ix, L, q0, nqc, safe, sms, st));
       if (sharded)
-        OM_TRY(exchange_chunk(ix, comm, L, q0, nqc, wide ? L.k : L.kc, dD, dI, id_offset, st));
+        OM_TRY(exchange_chunk(ix, comm, L, q0, nqc, dD, dI, id_offset, st));
       else
         OM_TRY(finalize_chunk(ix, L, q0, nqc, dD + static_cast<size_t>(q0) * L.k, dI + static_cast<size_t>(q0) * L.k, L.k,
                               id_offset, nullptr, nullptr, nullptr, nullptr, st));
       if (certify) {
         Timed t(ix, st, 3);
+        const ExchangeBlock b = exchange_block(nqc, L.kc);
+        const float* floors = sharded ? reinterpret_cast<const float*>(L.recv + b.off_floor) : L.thr;
+        const float* gst = sharded ? reinterpret_cast<const float*>(L.recv + b.off_stats) : ix->gstats;
         certify_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(dD + static_cast<size_t>(q0) * L.k, dI + static_cast<size_t>(q0) * L.k,
-                                                      L.k, L.thr, sharded ? L.range : nullptr, sharded ? L.hist : nullptr,
-                                                      L.kp_target, L.hn + q0, L.en + q0,
-                                                      sharded ? L.range + 2 * nqc : ix->gstats, ix->d, nqc, q0, flags,
-                                                      L.status + 2);
+                                                      L.k, floors, static_cast<int64_t>(b.bytes / 4), sharded ? comm->world : 1,
+                                                      gst, static_cast<int64_t>(b.bytes / 4), L.hn + q0, L.en + q0, ix->d, nqc,
+                                                      q0, flags, L.status + 2);
         OM_CUDA(cudaGetLastError());
         ix->st_launches += 1;
       }
     }
-    if (sharded)  // every rank must take the same retry decision
-      OM_NCCL(nccl_api().AllReduce(L.status, L.status, 2, kNcclInt32, kNcclMax, comm->nccl, st));
+    if (sharded)  // every rank must take the same retry decision (list overflow on any shard)
+      OM_NCCL(nccl_api().AllReduce(L.status, L.status, 1, kNcclInt32, kNcclMax, comm->nccl, st));
     OM_CUDA(cudaMemcpyAsync(ix->h_status, L.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     OM_CUDA(cudaStreamSynchronize(st));
     const unsigned int fault = read_clear_dev_fault();
@@ -1219,11 +1221,6 @@ int run_level(om_index* ix, om_comm* comm, Level& L, float* dD, int64_t* dI, int
       if (safe) return fail(OM_EFAULT, "candidate list overflow in the overflow-proof schedule (bug)");
       safe = true;
       ix->st_retries++;
-      continue;
-    }
-    if (ix->h_status[1] && !wide) {
-      wide = true;
-      ix->st_wide_exchange++;
       continue;
     }
     *nflag_out = certify ? ix->h_status[2] : 0;
@@ -1322,7 +1319,9 @@ int search_impl(om_index* ix, om_comm* comm, const void* q, om_memkind q_kind, i
     OM_TRY(run_sub(nullptr, nq, k, 1, &dummy));
   } else if (nf > 0) {
     const int* list = flag_list;
-    if (kp0 < kMaxCandidates && ix->n > kp0) {  // level 1: widest candidate list the select / sort kernels take
+    // level 1: widest candidate list the select / sort kernels take.  (Sharded: the decision must not depend on this
+    // rank's row count — every rank runs the same levels.)
+    if (kp0 < kMaxCandidates && (world > 1 || ix->n > kp0)) {
       int nf1 = 0;
       OM_TRY(run_sub(list, nf, kMaxCandidates, 0, &nf1));
       if (nf1 > 0) {

@@ -324,7 +324,7 @@ static void perf_case(const char* name, int M, int N, int K, int num_sms, int it
 }
 
 // the product's scan epilogue on the search shape, thresholds set so that nothing survives
-template <int EW, int VARIANT = 0>
+template <int EW, int VARIANT = 0, bool F16 = false>
 static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value, bool dyn = false,
                       std::vector<unsigned long long>* keys_out = nullptr) {
   __nv_bfloat16 *dA, *dB;
@@ -358,10 +358,10 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 2; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32, VARIANT>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32, VARIANT>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -377,7 +377,7 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   surv /= (iters + 2);
   if (keys_out) {  // survivors of ONE launch, sorted per query: identical across filter variants by construction
     CK(cudaMemset(count, 0, M * 4));
-    CK((launch_gemm<256, 4, true, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
+    CK((launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32, VARIANT>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
     CK(cudaDeviceSynchronize());
     std::vector<int> c1(M);
     CK(cudaMemcpy(c1.data(), count, M * 4, cudaMemcpyDeviceToHost));
@@ -446,6 +446,14 @@ int main(int argc, char** argv) {
          prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
   const int sms = prop.multiProcessorCount;
   int fails = 0;
+  if (argc > 1 && strcmp(argv[1], "--f16cmp") == 0) {
+    // fp16 vs bf16 operands on the scan shape, long enough to sit in the power-capped (sustained) regime
+    for (int rep = 0; rep < 2; ++rep) {
+      perf_scan<8, 0, false>("bf16 sustained 4M", 6980, 1 << 22, 768, sms, 12, 42.f, true);
+      perf_scan<8, 0, true>("fp16 sustained 4M", 6980, 1 << 22, 768, sms, 12, 42.f, true);
+    }
+    return 0;
+  }
   if (argc > 1 && strcmp(argv[1], "--scanvar") == 0) {
     const int fv = run_scan_variants(sms);
     printf("scanvar: %d failing check(s)\n", fv);

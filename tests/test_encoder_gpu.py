@@ -174,6 +174,40 @@ def test_bert_large_shape(enc_mod):
     _check(reps.cpu().numpy(), oreps.numpy(), "reps (bert-large width)")
 
 
+def test_bert_large_full_depth_vs_oracle(enc_mod):
+    # BASELINE.json configs[4]'s encoder: all 24 layers of bert-large (1024 hidden, 16 heads, 4096 ffn), ragged batch
+    gen = torch.Generator().manual_seed(24)
+    layers, H, F, vocab = 24, 1024, 4096, 1200
+    sd = _rand_bert_sd(gen, layers, H, F, vocab, 128)
+    spec = dict(arch="bert", layers=layers, hidden=H, heads=16, ffn=F, vocab=vocab, max_pos=128, type_vocab=2,
+                ln_eps=1e-12)
+    enc = enc_mod.CudaEncoder(spec, sd, pooling="first", max_batch_tokens=1024)
+    ids, mask = _ids(gen, 6, 48, vocab)
+    reps = enc.encode(ids.cuda(), mask.cuda())
+    _, oreps = oracle.encode_reps(sd, EncoderSpec("bert", layers, H, 16, F, 1e-12), ids, mask)
+    _check(reps.cpu().numpy(), oreps.numpy(), "reps (bert-large, 24 layers)")
+
+
+def test_bench_sized_batch_vs_oracle(enc_mod):
+    # the batch geometry bench.py runs — B = 256 x L = 128 = 32 768 tokens, 256 m-tiles, every GEMM several waves deep,
+    # the static tile schedule and the residual epilogue's next-tile prefetch all exercised — on 2 layers (the CPU oracle
+    # finishes in seconds); every 7th sequence is checked
+    gen = torch.Generator().manual_seed(256)
+    layers, H, F, vocab = 2, 768, 3072, 2500
+    sd = _rand_bert_sd(gen, layers, H, F, vocab, 128)
+    spec = dict(arch="bert", layers=layers, hidden=H, heads=12, ffn=F, vocab=vocab, max_pos=128, type_vocab=2,
+                ln_eps=1e-12)
+    enc = enc_mod.CudaEncoder(spec, sd, pooling="first", max_batch_tokens=256 * 128)
+    ids, mask = _ids(gen, 256, 128, vocab)
+    reps = enc.encode(ids.cuda(), mask.cuda()).cpu().numpy()
+    sel = list(range(0, 256, 7))
+    _, oreps = oracle.encode_reps(sd, EncoderSpec("bert", layers, H, 12, F, 1e-12), ids[sel], mask[sel])
+    _check(reps[sel], oreps.numpy(), "reps (B = 256)")
+    # batch composition must not matter: the same sequences encoded alone give the same representations
+    alone = enc.encode(ids[sel].cuda(), mask[sel].cuda()).cpu().numpy()
+    np.testing.assert_allclose(alone, reps[sel], rtol=0, atol=2e-2)
+
+
 @pytest.mark.parametrize("L,B", [(128, 4), (32, 7), (50, 3)])
 def test_t5_base_vs_oracle(enc_mod, L, B):
     gen = torch.Generator().manual_seed(200 + L)
