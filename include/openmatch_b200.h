@@ -118,7 +118,7 @@ int om_index_search(om_index* idx, const void* q, om_memkind q_kind, int nq, int
 /* Row-sharded search with the exchange inside the library — replaces faiss.index_cpu_to_gpu_multiple(shard=True) +
  * IndexShards (src/openmatch/retriever/dense_retriever.py:43-58).  One process per GPU; every rank holds a contiguous
  * row shard and calls om_index_search_sharded with the same queries and its own id_offset; every rank receives the
- * same global (D, I).  Each shard keeps a candidate list sized for its share of the answer (1.5 (k + slack) / world + 64
+ * same global (D, I).  Each shard keeps a candidate list sized for its share of the answer (m + 6 sqrt(m) + 32 with m = (k + slack) / world
  * rows), re-scores it in fp32 and ships it whole together with the list's stage-score floor and the shard's error-norm
  * maxima in ONE packed NCCL all-gather per query chunk (issued on `stream` between the kernels, single host
  * synchronisation at the end of a level); every rank merges the lists and runs the exactness certificate of
@@ -156,7 +156,7 @@ int om_index_search_finish(om_index* idx, const float* global_range, const int* 
 int om_search_floor_bins(void);
 /* Tunables: "rescore_slack" (extra candidate-stage rows kept per query; default max(128, k/5)),
  * "force_safe_rounds" (1 = always use the overflow-proof fixed-size round schedule; testing),
- * "round_growth" (2..8, default 2: each scan round covers (g-1) x the rows already seen),
+ * "round_growth" (2..8: each scan round covers (g-1) x the rows already seen; default 0 = auto: 2, or 8 for <= 256 queries),
  * "certify" (default 1; 0 = skip the exactness certificate and its escalation: top-k of the fp16 candidate stage),
  * "exact_only" (1 = answer every query with the exact fp32 CUDA-core scan; testing),
  * "debug_stage_scores" (1 = D holds candidate-stage scores instead of fp32 re-scores; error-model measurement),

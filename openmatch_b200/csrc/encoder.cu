@@ -1565,6 +1565,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     const float* b_in = bert ? (li == 0 ? e->emb_b : e->layers[li - 1].ln2_b) : nullptr;
     {
       EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv_fold : nullptr, T, 2 * I, ap.Tvalid_rows, normA};
+      // (192-wide tiles with 12 epilogue warps measured 3 % slower here and on FFN1: r02 tile A/B in profiles/README.md)
       cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
       if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
     }

@@ -28,6 +28,7 @@
 //              always the exact top-k by fp32 inner product, ties by row id — never "top-k up to fp16 noise".
 #include <cuda_fp16.h>
 #include <float.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -705,7 +706,9 @@ struct om_index {
   int64_t rescore_slack = -1;
   int force_safe = 0;
   int dynamic_sched = 1;  // claim scan tiles from a global counter (keeps CTAs on neighbouring corpus tiles)
-  int growth = 2;         // each round scans (growth - 1) x the rows seen so far (2 measured best on B200)
+  int growth = 0;         // each round scans (growth - 1) x the rows seen so far; 0 = auto: 2 for query batches (measured
+                          // best at nq = 6 980: fewest filter survivors), 8 for <= 256 queries (HBM-bound streaming
+                          // regime: 5 instead of 13 dependent scan + select launch pairs over 8.8 M rows)
   int certify = 1;        // 0: legacy behaviour (top-k of the half-precision candidate stage, no proof)
   int exact_only = 0;     // 1: answer every query with the exact fp32 scan (testing / reference timing)
   int stage_scores = 0;   // 1: emit candidate-stage scores instead of fp32 re-scores (measuring the error model)
@@ -861,7 +864,7 @@ int om_index_set_param(om_index* ix, const char* name, int64_t value) {
   } else if (!strcmp(name, "force_safe_rounds")) {
     ix->force_safe = value != 0;
   } else if (!strcmp(name, "round_growth")) {
-    if (value < 2 || value > 8) return fail(OM_EINVAL, "round_growth must be in [2, 8]");
+    if (value != 0 && (value < 2 || value > 8)) return fail(OM_EINVAL, "round_growth must be 0 (auto) or in [2, 8]");
     ix->growth = static_cast<int>(value);
   } else if (!strcmp(name, "dynamic_sched")) {
     ix->dynamic_sched = value != 0;
@@ -982,16 +985,18 @@ int level_prepare(om_index* ix, Level& L, const float* qf, int nq, int k, int kp
   L.mode = mode;
   L.world = world;
   L.kp_target = std::min(std::max(kp_target, k), kMaxCandidates);
-  // Row-sharded search: the global top-(k + slack) draws ~(k + slack) / W rows from every shard, so each shard keeps a
-  // list of 1.5x that + 64 instead of k + slack: scan survivors, select and re-score work all shrink W-fold and the whole
-  // list is shipped (no agreement phase).  A shard that holds more of the answer than its list (skewed shards) shows up
+  // Row-sharded search: the global top-(k + slack) draws ~(k + slack) / W rows from every shard (binomial: mean m = kp / W,
+  // deviation sqrt(m)), so each shard keeps a list of m + 6 sqrt(m) + 32 rows instead of k + slack: scan survivors, select
+  // and re-score work all shrink W-fold and the whole list is shipped (no agreement phase).  A shard that holds more of the answer than its list (skewed shards) shows up
   // as a high floor: the certificate fails and the query is escalated to the 4096-wide level, which keeps full lists.
-  if (world > 1 && mode == 0 && L.kp_target < kMaxCandidates)
-    L.kp_target = static_cast<int>(std::min<int64_t>(L.kp_target, round_up((3 * static_cast<int64_t>(L.kp_target)) / (2 * world) + 64, 32)));
+  if (world > 1 && mode == 0 && L.kp_target < kMaxCandidates) {
+    const double m = static_cast<double>(L.kp_target) / world;
+    L.kp_target = static_cast<int>(std::min<int64_t>(L.kp_target, round_up(static_cast<int64_t>(m + 6.0 * sqrt(m) + 32.0), 32)));
+  }
   L.kp = static_cast<int>(std::min<int64_t>(L.kp_target, std::max<int64_t>(ix->n, 1)));
   // Expected list length after a round that multiplies the rows seen by g is ~g kp (kp kept + ~(g-1) kp new
   // survivors); 25 % + 512 entries of head-room cover its spread for exchangeable row order.
-  for (L.growth = ix->growth;; --L.growth) {  // large k: slower-growing schedule that fits the 16384-entry select
+  for (L.growth = ix->growth > 0 ? ix->growth : (nq <= 256 ? 8 : 2);; --L.growth) {  // large k: slower-growing schedule that fits the 16384-entry select
     L.C = 1024;
     while (L.C < (5 * L.growth * L.kp) / 4 + 512) L.C <<= 1;
     if (L.C <= 16384 || L.growth == 2) break;

@@ -93,17 +93,19 @@ x[dup] = v + 1e-4 * rng.standard_normal((9000, d), dtype=np.float32)
 q = (v + 0.1 * rng.standard_normal((nq, d), dtype=np.float32)).astype(np.float32)
 idx = sharded(x, uneven(n))
 D, I = idx.search(q, k)
-assert idx.local.stat("exact_queries") == nq, "expected the exact level, stats: uncertified %d wide %d exact %d" % (
-    idx.local.stat("uncertified"), idx.local.stat("uncertified_wide"), idx.local.stat("exact_queries"))
+stats3 = tuple(idx.local.stat(s) for s in ("uncertified", "uncertified_wide", "exact_queries"))
+assert stats3[0] == nq, "the first level cannot certify a near-duplicate cluster: %s" % (stats3,)
+if 9000 // world > 4096:  # more duplicates per shard than the widest list holds: only the exact scan can answer
+    assert stats3[2] == nq, "expected the exact level, stats (uncertified, wide, exact): %s" % (stats3,)
 one = FlatIPIndex(d)
 one.add(x)
 D1, I1 = one.search(q, k)
 assert (I == I1).all() and (D == D1).all()
 eps_check(q, x, D, I, k, 2e-6)
-report.append("near-duplicates exact")
+report.append("near-duplicates exact (uncertified %d, after wide level %d, exact scan %d)" % stats3)
 del one
 
-# ---- 4. skewed shards: every relevant row lives on the last rank, whose shard-sized list (1.5 kp / W + 64 < k) cannot
+# ---- 4. skewed shards: every relevant row lives on the last rank, whose shard-sized list (kp / W + 6 sigma + 32 < k) cannot
 #         hold the answer -> its floor is high, the certificate fails, the 4096-wide level answers ----
 n, d, nq, k = 30000, 64, 9, 1000
 x = rng.integers(-3, 4, (n, d)).astype(np.float32)

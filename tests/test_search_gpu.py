@@ -413,3 +413,22 @@ def test_stage_error_model_holds_on_hardware(om, d):
         stage = dict(zip(Is[r].tolist(), Ds[r].tolist()))
         diff = [abs(stage[i] - s) for i, s in zip(I[r].tolist(), D[r].tolist()) if i in stage]
         assert max(diff) < E
+
+
+def test_round_growth_settings_agree(om):
+    # the round schedule (auto: x8 for small query batches, x2 for large ones) only changes how the corpus is swept
+    rng = np.random.default_rng(44)
+    x, q = _int_data(rng, 150000, 64, -6, 6), _int_data(rng, 19, 64, -6, 6)
+    D0, I0 = oracle.flat_ip_search(q, x, 300)
+    idx = om.FlatIPIndex(64)
+    idx.add(x)
+    rounds = {}
+    for g in (0, 2, 3, 8):
+        idx.set_param("round_growth", g)
+        D, I = idx.search(q, 300)
+        np.testing.assert_array_equal(I, I0)
+        np.testing.assert_array_equal(D, D0)
+        rounds[g] = idx.stat("rounds")
+    assert rounds[0] == rounds[8] < rounds[3] < rounds[2]
+    with pytest.raises(RuntimeError):
+        idx.set_param("round_growth", 9)
