@@ -302,10 +302,15 @@ def main():
         I_out = torch.empty((nq, k), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
+    # device results go into tensors allocated ONCE: a fresh [nq, k] pair per step made the caching allocator call
+    # cudaMalloc inside the second timed step (the first pair still being referenced): a 15 - 100 ms stall in every run
+    D_dev = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    I_dev = torch.empty((nq, k), dtype=torch.int64, device=dev)
+
     def search_step(q):
         if world == 1:
-            return idx.search_device(q, k, id_offset=lo)
-        return idx.search_sharded_device(comm, q, k, lo)
+            return idx.search_device(q, k, id_offset=lo, out=(D_dev, I_dev))
+        return idx.search_sharded_device(comm, q, k, lo, out=(D_dev, I_dev))
 
     def e2e_step():
         if world == 1:
@@ -316,7 +321,7 @@ def main():
     # ---------------- device-resident search (value) + per-kernel device time for the roofline ----------------
     idx.set_param("profile", 1)
     acc = {"scan_ns": 0, "select_ns": 0, "finalize_ns": 0, "other_ns": 0, "launches": 0, "uncertified": 0, "exact_queries": 0,
-           "wide_exchanges": 0, "overflow_retries": 0}
+           "overflow_retries": 0}
     rounds = 0
     last = {}
 
@@ -421,8 +426,9 @@ def main():
                                % (wl["name"], k, total_rows, d, nq), "corpus_rows": total_rows, "rows_per_gpu": n_local, "dim": d,
                    "k": k, "nq": nq, "candidate_stage": "fp16 tensor-core scan (fp32 accumulate) + fp32 re-score + exactness "
                    "certificate (escalation: 4096-wide list, then exact fp32 scan)", "rounds": rounds,
-                   "parallelism": ("index row-sharded x%d, om_index_search_sharded: NCCL all-reduce of score range + histogram, "
-                                   "packed all-gather of a fixed-width prefix, merge + certificate on every rank" % world)
+                   "parallelism": ("index row-sharded x%d, om_index_search_sharded: shard-sized candidate lists, ONE packed NCCL "
+                                   "all-gather per query chunk (scores | ids | floors | error norms), merge + certificate on "
+                                   "every rank" % world)
                    if world > 1 else "single shard",
                    "l2_policy": "inputs_exceed_l2 (fp16 scan copy %.1f GB per GPU)" % (n_local * d * 2 / 1e9)},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * d * 4,
@@ -439,7 +445,7 @@ def main():
                      "non_scan_ms_per_step": ms_per_step - phase["scan"]},
         "certificate": {"uncertified_queries_per_step": acc["uncertified"] / args.steps,
                         "exact_scan_queries_per_step": acc["exact_queries"] / args.steps,
-                        "wide_exchanges": acc["wide_exchanges"], "overflow_retries": acc["overflow_retries"]},
+                        "overflow_retries": acc["overflow_retries"]},
         "clocks": clocks.summary(),
         "step_wall_ms": step_wall,
     }
@@ -775,14 +781,16 @@ def c5_shard_leg(torch, fill_index, timed, nq, k, dev, peaks):
     scan_ns = 0
     unc = 0
 
+    out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev))
+
     def step():
         nonlocal scan_ns, unc
-        idx.search_device(q, k)
+        idx.search_device(q, k, out=out)
         scan_ns += idx.stat("scan_ns")
         unc += idx.stat("uncertified")
 
     for _ in range(2):
-        idx.search_device(q, k)
+        idx.search_device(q, k, out=out)
     ms = timed(step, 3, 0) / 3
     ach = 2.0 * nq * n * d * 3 / (scan_ns * 1e-9) / 1e12
     out = {"rows": n, "dim": d, "nq": nq, "k": k, "ms_per_step": ms, "queries_per_s": nq / (ms * 1e-3),

@@ -79,24 +79,34 @@ class FlatIPIndex:
         return D, I
 
     # ---- device-resident variants ----
-    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    @staticmethod
+    def _outputs(nq: int, k: int, device, out):
+        if out is None:
+            return (torch.empty((nq, k), dtype=torch.float32, device=device),
+                    torch.empty((nq, k), dtype=torch.int64, device=device))
+        D, I = out
+        if D.shape != (nq, k) or I.shape != (nq, k) or D.dtype != torch.float32 or I.dtype != torch.int64 or \
+                not (D.is_cuda and I.is_cuda and D.is_contiguous() and I.is_contiguous()):
+            raise ValueError("out must be contiguous CUDA tensors (float32 [nq, k], int64 [nq, k])")
+        return D, I
+
+    def search_device(self, q: torch.Tensor, k: int, id_offset: int = 0, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``out=(D, I)``: write into caller-owned CUDA tensors (no allocation on the search path)."""
         q = q.contiguous().float()
         self._check_shape(q.shape)
         nq = q.shape[0]
-        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        D, I = self._outputs(nq, int(k), q.device, out)
         _lib.check(self._lib.om_index_search(self._h, q.data_ptr(), _lib.OM_DEVICE, nq, int(k), D.data_ptr(),
                                              I.data_ptr(), _lib.OM_DEVICE, int(id_offset), _stream()))
         return D, I
 
-    def search_sharded_device(self, comm: "Comm", q: torch.Tensor, k: int, id_offset: int = 0):
+    def search_sharded_device(self, comm: "Comm", q: torch.Tensor, k: int, id_offset: int = 0, out=None):
         """This rank's call of the row-sharded search (``om_index_search_sharded``): collective over ``comm``; every
         rank passes the same queries and receives the same global (D, I) [nq, k] on its device."""
         q = q.contiguous().float()
         self._check_shape(q.shape)
         nq = q.shape[0]
-        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        D, I = self._outputs(nq, int(k), q.device, out)
         _lib.check(self._lib.om_index_search_sharded(self._h, comm._h, q.data_ptr(), _lib.OM_DEVICE, nq, int(k),
                                                      D.data_ptr(), I.data_ptr(), _lib.OM_DEVICE, int(id_offset), _stream()))
         return D, I
