@@ -43,18 +43,11 @@ __host__ __device__ __forceinline__ float key_score(unsigned long long k) {
 // ---------------------------------------------------------------------------------------------------
 // fused scan epilogue
 // ---------------------------------------------------------------------------------------------------
-// VARIANT selects the filter's code shape for the sparse rounds (same results, different cost per survivor):
-//   0  shipped: one 32-column max, then a 32-bit mask and a 31-SEL select tree per survivor
-//   1  candidate for the next round (unmeasured): 4 group maxima of 8 columns; only groups that beat the
-//      threshold are expanded (8-bit mask, 7-SEL tree), the group's 8 values chosen by a select on the group id
-//   2  candidate (unmeasured): like 1 with the four group bodies unrolled (no group select, more cold code)
-//   3  candidate (unmeasured): warp-cooperative extraction - a lane whose chunk beats its threshold broadcasts its
-//      32 values with 32 shuffles so that lane i holds column i; one compare + ballot finds every survivor of the
-//      chunk at once and the surviving lanes store their own keys (no mask loop, no select tree, no single-lane
-//      dependent chain; cost independent of the number of survivors in the chunk)
-// Measured with selftest perf_scan (variant 0): 1 survivor per warp-tile costs ~15 % of the scan rate, i.e. about
-// a thousand cycles of a single-lane dependent chain per survivor - the term to shrink.
-template <bool DENSE, int EPI_THREADS = 256, int VARIANT = 0>
+// Filter shape: one 32-column max (3-input max tree), then a 32-bit mask and a 31-SEL select tree per survivor.  Three
+// alternative shapes (group maxima of 8 columns with 8-bit masks, rolled or unrolled; warp-cooperative extraction with
+// shuffles + ballot) were measured in round 2 against this one at five survivor densities: all within +-1 %
+// (profiles/r02_scan_variants_selftest.log), the warp-cooperative one 13 % slower at high density — removed.
+template <bool DENSE, int EPI_THREADS = 256>
 struct EpiScan {
   const float* thr;          // [nq] strict lower bound per query
   unsigned long long* cand;  // [nq, C]
@@ -134,10 +127,6 @@ struct EpiScan {
     }
   }
   __device__ __forceinline__ void chunk(State& s, int row, int col0, const float (&v)[32], int pass) const {
-    if constexpr (VARIANT == 3 && !DENSE) {
-      chunk_coop(s, row, col0, v, pass);  // warp-collective: every lane stays in
-      return;
-    }
     if (row >= nq || col0 >= n_cols) return;
     unsigned long long* mine = cand + static_cast<size_t>(row) * C;
     if constexpr (DENSE) {
@@ -159,10 +148,6 @@ struct EpiScan {
     const float t = s.t;
     const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
     if (pass == 1 && s.n <= kStash) return;
-    if constexpr (VARIANT != 0) {
-      chunk_grouped(s, row, col0, v, pass, t, lim, mine);
-      return;
-    }
     float mx = v[0];
 #pragma unroll
     for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
@@ -191,134 +176,6 @@ struct EpiScan {
       } else {
         if (s.pos2 < C) mine[s.pos2] = key;
         ++s.pos2;
-      }
-    }
-  }
-  // one survivor: column col (absolute within the round) with score val
-  __device__ __forceinline__ void keep(State& s, float val, int col, int pass, unsigned long long* mine) const {
-    const unsigned long long key = make_key(val, row_base + col);
-    if (pass == 0) {
-      if (s.k < kStash) {
-        *slot(s, s.buf, s.k) = key;
-        ++s.k;
-      }
-      ++s.n;
-    } else if (s.skip > 0) {
-      --s.skip;
-    } else {
-      if (s.pos2 < C) mine[s.pos2] = key;
-      ++s.pos2;
-    }
-  }
-  // w[j] for a run-time j in [0, 8): 3-level select tree (7 SEL)
-  __device__ __forceinline__ static float pick8(const float (&w)[8], int j) {
-    float a[4], b[2];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = (j & 1) ? w[2 * u + 1] : w[2 * u];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) b[u] = (j & 2) ? a[2 * u + 1] : a[2 * u];
-    return (j & 4) ? b[1] : b[0];
-  }
-  __device__ __forceinline__ void expand_group(State& s, const float (&w)[8], int col_g, int lim_g, float t, int pass,
-                                               unsigned long long* mine) const {
-    uint32_t m8 = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m8 |= (w[j] > t ? 1u : 0u) << j;
-    if (lim_g < 8) m8 &= lim_g > 0 ? (1u << lim_g) - 1u : 0u;
-#pragma unroll 1
-    while (m8) {
-      const int j = __ffs(m8) - 1;
-      m8 &= m8 - 1;
-      keep(s, pick8(w, j), col_g + j, pass, mine);
-    }
-  }
-  // VARIANT 1 / 2 (see the struct comment); visits survivors in increasing column order like variant 0
-  __device__ __forceinline__ void chunk_grouped(State& s, int row, int col0, const float (&v)[32], int pass, float t,
-                                                int lim, unsigned long long* mine) const {
-    float g[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float m1 = fmaxf(fmaxf(v[8 * q], v[8 * q + 1]), v[8 * q + 2]);
-      const float m2 = fmaxf(fmaxf(v[8 * q + 3], v[8 * q + 4]), v[8 * q + 5]);
-      g[q] = fmaxf(fmaxf(fmaxf(m1, m2), v[8 * q + 6]), v[8 * q + 7]);
-    }
-    const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-    if (!(mx > t)) return;  // common case: nothing in this chunk beats the threshold
-    if constexpr (VARIANT == 2) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (g[q] > t) {
-          float w[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = v[8 * q + j];
-          expand_group(s, w, col0 + 8 * q, lim - 8 * q, t, pass, mine);
-        }
-      }
-    } else {
-      uint32_t gm = (g[0] > t ? 1u : 0u) | (g[1] > t ? 2u : 0u) | (g[2] > t ? 4u : 0u) | (g[3] > t ? 8u : 0u);
-#pragma unroll 1
-      while (gm) {
-        const int q = __ffs(gm) - 1;
-        gm &= gm - 1;
-        float w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float lo = (q & 1) ? v[8 + j] : v[j], hi = (q & 1) ? v[24 + j] : v[16 + j];
-          w[j] = (q & 2) ? hi : lo;
-        }
-        expand_group(s, w, col0 + 8 * q, lim - 8 * q, t, pass, mine);
-      }
-    }
-  }
-  // VARIANT 3 (see the struct comment).  Must be called by all 32 lanes of the warp (the GEMM epilogue loop is
-  // warp-uniform).  Survivors are appended in increasing column order, exactly like variant 0.
-  __device__ __forceinline__ void chunk_coop(State& s, int row, int col0, const float (&v)[32], int pass) const {
-    const unsigned full = 0xffffffffu;
-    const int lane = static_cast<int>(threadIdx.x & 31u);
-    if (col0 >= n_cols) return;  // warp-uniform
-    const bool active = row < nq && !(pass == 1 && s.n <= kStash);
-    float mx = v[0];
-#pragma unroll
-    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
-    unsigned hot = __ballot_sync(full, active && mx > s.t);
-    if (hot == 0u) return;  // common case: no lane of the warp has a survivor in this chunk
-    const int lim = n_cols - col0;  // columns >= lim are out of range (only in the last tile)
-#pragma unroll 1
-    while (hot) {
-      const int L = __ffs(hot) - 1;  // the lane (query row) being expanded
-      hot &= hot - 1;
-      float x = 0.f;  // lane i receives column i of lane L's chunk
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float y = __shfl_sync(full, v[i], L);
-        if (lane == i) x = y;
-      }
-      const float tL = __shfl_sync(full, s.t, L);
-      const int rowL = __shfl_sync(full, row, L);
-      const bool sv = x > tL && lane < lim;
-      const unsigned m = __ballot_sync(full, sv);
-      const int cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
-      const unsigned long long key = make_key(x, row_base + col0 + lane);
-      if (pass == 0) {
-        const int kL = __shfl_sync(full, s.k, L), bufL = __shfl_sync(full, s.buf, L);
-        const int j = kL + rank;
-        if (sv && j < kStash)
-          s.stash[(static_cast<size_t>(bufL) * kStash + j) * kEpiThreads + (s.tid - lane + L)] = key;
-        if (lane == L) {
-          s.k = kL + cnt < kStash ? kL + cnt : kStash;
-          s.n += cnt;
-        }
-      } else {
-        const int skipL = __shfl_sync(full, s.skip, L), posL = __shfl_sync(full, s.pos2, L);
-        if (sv && rank >= skipL) {
-          const int p = posL + (rank - skipL);
-          if (p < C) cand[static_cast<size_t>(rowL) * C + p] = key;
-        }
-        if (lane == L) {
-          const int used = cnt < skipL ? cnt : skipL;
-          s.skip = skipL - used;
-          s.pos2 = posL + (cnt - used);
-        }
       }
     }
   }
