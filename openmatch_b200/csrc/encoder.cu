@@ -634,7 +634,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(128, 4)
-attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt, AttnParams p) {
+attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVt, AttnParams p, int n_tiles,
+            int n_heads) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_kb = reinterpret_cast<float*>(smem + kAttnSmemMisc);
@@ -643,8 +644,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile = blockIdx.x, head = blockIdx.y;
-  const int row0 = tile * p.Tvalid_rows;  // first token of this tile
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQK);
@@ -658,6 +657,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
     tmem_alloc(tmem_slot, kAttnTmemCols);
     tmem_relinquish();
   }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // Persistent CTA (grid = 4 per SM): barriers, tensor memory and descriptors are set up once; work items are
+  // (tile, head) pairs taken head-fastest, so that the CTAs running at the same time read the same token rows of qk
+  // (neighbouring 128-byte slices of one DRAM page instead of one slice from each of many pages).
+  const int n_items = n_tiles * n_heads;
+  uint32_t par = 0;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1u) {
+  const int tile = item / n_heads, head = item - tile * n_heads;
+  const int row0 = tile * p.Tvalid_rows;  // first token of this tile
+  if (tid == 0) {  // shared memory and tensor memory of the previous item are free (trailing barrier): loads go out first
+    mbar_arrive_expect_tx(&bars[0], 3 * 16384);
+    tma_load_2d(smem + kAttnSmemQ, &tmQK, &bars[0], head * kHeadDim, row0);
+    tma_load_2d(smem + kAttnSmemK, &tmQK, &bars[0], p.I + head * kHeadDim, row0);
+    tma_load_2d(smem + kAttnSmemV, &tmVt, &bars[0], tile * 128, head * kHeadDim);
+    tma_load_2d(smem + kAttnSmemV + 8192, &tmVt, &bars[0], tile * 128 + 64, head * kHeadDim);
+  }
   {
     const int tok = row0 + tid;
     // key validity as 4 x 32-bit words (bit c%32 of word c/32): one ballot per warp
@@ -668,18 +687,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
       for (int i = tid; i < 2 * kMaxL - 1; i += 128) s_rel[i] = p.relbias_log2[head * (2 * kMaxL - 1) + i];
     }
   }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  __syncthreads();  // key bits / relative bias of this item are in place
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], 3 * 16384);
-    tma_load_2d(smem + kAttnSmemQ, &tmQK, &bars[0], head * kHeadDim, row0);
-    tma_load_2d(smem + kAttnSmemK, &tmQK, &bars[0], p.I + head * kHeadDim, row0);
-    tma_load_2d(smem + kAttnSmemV, &tmVt, &bars[0], tile * 128, head * kHeadDim);
-    tma_load_2d(smem + kAttnSmemV + 8192, &tmVt, &bars[0], tile * 128 + 64, head * kHeadDim);
-    mbar_wait(&bars[0], 0, 10);
+    mbar_wait(&bars[0], par, 10);
     tc_fence_after_sync();
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     const uint32_t qa = smem_u32(smem + kAttnSmemQ), ka = smem_u32(smem + kAttnSmemK);
@@ -689,7 +700,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
                    umma_smem_desc(ka + k * 32, kDescKMajorSW128), idesc_s, k != 0 ? 1u : 0u);
     umma_commit(&bars[1]);
   }
-  mbar_wait_warp(&bars[1], 0, 11);
+  mbar_wait_warp(&bars[1], par, 11);
   tc_fence_after_sync();
 
   // ---- softmax: thread r owns query row r of the tile ----
@@ -773,7 +784,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
                    umma_smem_desc(va + (k >> 2) * 8192 + (k & 3) * 32, kDescKMajorSW128), idesc_o, k != 0 ? 1u : 0u);
     umma_commit(&bars[2]);
   }
-  mbar_wait_warp(&bars[2], 0, 12);
+  mbar_wait_warp(&bars[2], par, 12);
   tc_fence_after_sync();
 #pragma unroll 1
   for (int c2 = 0; c2 < 2; ++c2) {
@@ -792,12 +803,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CU
       }
     }
   }
+  // the next item's TMA loads overwrite Q / K / V and its first MMA overwrites S: every thread must be done with O
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kAttnTmemCols);
-  }
+  tc_fence_after_sync();
+  }  // item loop
+  if (warp == 0) tmem_dealloc(tmem_base, kAttnTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1572,7 +1583,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     if (long_seq)
       attn_long_kernel<<<dim3(n_tiles, d.heads), 128, kAttnLongSmemBytes, st>>>(tmQK, tmVt, ap);
     else
-      attn_kernel<<<dim3(n_tiles, d.heads), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap);
+      attn_kernel<<<std::min(n_tiles * d.heads, sms * 4), 128, kAttnSmemBytes, st>>>(tmQK, tmVt, ap, n_tiles, d.heads);
     OM_CUDA(cudaGetLastError());
     {
       // s <- ctx Wo^T + bo + LN_in(s) (BERT) / + s (T5); statistics of the new s -> stats[1]
