@@ -432,3 +432,23 @@ def test_round_growth_settings_agree(om):
     assert rounds[0] == rounds[8] < rounds[3] < rounds[2]
     with pytest.raises(RuntimeError):
         idx.set_param("round_growth", 9)
+
+
+def test_more_queries_than_one_chunk(om):
+    # 20 000 queries: two query chunks (16 384 + 3 616) through scan / select / re-score / certificate, host and device paths
+    rng = np.random.default_rng(99)
+    x, q = _int_data(rng, 3000, 64, -7, 7), _int_data(rng, 20000, 64, -7, 7)
+    idx = om.FlatIPIndex(64)
+    idx.add(x)
+    D, I = idx.search(q, 7)
+    D0, I0 = oracle.flat_ip_search(q, x, 7)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+    Dd, Id = idx.search_device(torch.from_numpy(q).cuda(), 7)
+    np.testing.assert_array_equal(Id.cpu().numpy(), I0)
+    # caller-owned output tensors
+    out = (torch.empty((20000, 7), dtype=torch.float32, device="cuda"), torch.empty((20000, 7), dtype=torch.int64, device="cuda"))
+    Do, Io = idx.search_device(torch.from_numpy(q).cuda(), 7, out=out)
+    assert Do.data_ptr() == out[0].data_ptr() and torch.equal(Io, Id) and torch.equal(Do, Dd)
+    with pytest.raises(ValueError):
+        idx.search_device(torch.from_numpy(q).cuda(), 7, out=(out[0][:5], out[1][:5]))
