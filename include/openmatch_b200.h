@@ -189,6 +189,9 @@ int om_topk_merge_n(const float* D_parts, const int64_t* I_parts, int nparts, in
 int om_contrastive_loss_fwd_bwd(const void* Q, const void* P, om_dtype dtype, int nq, int np, int d,
                                 const int64_t* target, int reduction, float loss_scale, float* loss_out,
                                 float* dQ, float* dP, float* scores_out, void* stream);
+/* Diagnostics: device time (ns, %globaltimer) the most recent loss call spent in its four phases
+ * {PREP, LOGITS, SOFTMAX, GRADS}.  Synchronous. */
+int om_debug_loss_phase_ns(uint64_t out[4]);
 
 #ifdef __cplusplus
 }

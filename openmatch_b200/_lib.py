@@ -63,6 +63,7 @@ SIGNATURES = {
     "om_topk_merge_n": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "om_contrastive_loss_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float,
                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "om_debug_loss_phase_ns": (c_int, [c_void_p]),
 }
 
 _lib = None

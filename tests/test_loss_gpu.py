@@ -31,7 +31,12 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("nq,n_p,d,dtype", [(64, 512, 768, torch.float32), (64, 512, 768, torch.bfloat16),
                                              (512, 4096, 768, torch.bfloat16), (5, 15, 24, torch.float32),
-                                             (8, 64, 32, torch.float32), (130, 1040, 1024, torch.float32)])
+                                             (8, 64, 32, torch.float32), (130, 1040, 1024, torch.float32),
+                                             # np > 4096 / np % 4 != 0: looped softmax; ragged K slices of dQ
+                                             (96, 4100, 200, torch.float32), (33, 2052, 72, torch.float32),
+                                             (40, 1001, 136, torch.float32),
+                                             # bf16 rows that TMA cannot read in place (pitch not 16-byte aligned)
+                                             (12, 24, 36, torch.bfloat16), (130, 1040, 200, torch.bfloat16)])
 def test_loss_and_grads_vs_oracle(L, nq, n_p, d, dtype):
     gen = torch.Generator().manual_seed(nq + d)
     x = (torch.randn(nq, d, generator=gen) * 0.5)
@@ -46,6 +51,22 @@ def test_loss_and_grads_vs_oracle(L, nq, n_p, d, dtype):
     np.testing.assert_allclose(scores.cpu().numpy(), want_s, rtol=1e-4, atol=1e-3)
     assert _rel(xg.grad.float().cpu().numpy(), want_dx) <= 1e-2
     assert _rel(yg.grad.float().cpu().numpy(), want_dy) <= 1e-2
+
+
+def test_gradients_are_run_to_run_identical(L):
+    # dQ is reduced over K slices computed by different CTAs: the slice order of the sum is fixed
+    gen = torch.Generator().manual_seed(9)
+    x = (torch.randn(512, 768, generator=gen) * 0.5).cuda().to(torch.bfloat16)
+    y = (torch.randn(4096, 768, generator=gen) * 0.5).cuda().to(torch.bfloat16)
+    outs = []
+    for _ in range(3):
+        xg, yg = x.clone().requires_grad_(), y.clone().requires_grad_()
+        loss = L.fused_contrastive_loss(xg, yg)
+        loss.backward()
+        outs.append((loss.item(), xg.grad.clone(), yg.grad.clone()))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0]
+        assert torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
 
 
 def test_reference_golden(L, golden_dir):
