@@ -708,7 +708,12 @@ def loss_leg(torch, timed, dev, eager):
                     lo_t.data_ptr(), dxq.data_ptr(), dxp.data_ptr(), None, om_lib.current_stream_ptr()))
 
         us = timed(loss_step, 3, 3) / 3 / reps * 1e3
-        loss_obj["shapes"][name] = {"us": us, "tflops": 6.0 * bq * bp * 768 / (us * 1e-6) / 1e12}
+        import ctypes
+        ph = (ctypes.c_uint64 * 4)()
+        om_lib.check(lib.om_debug_loss_phase_ns(ph))
+        loss_obj["shapes"][name] = {"us": us, "tflops": 6.0 * bq * bp * 768 / (us * 1e-6) / 1e12,
+                                    "phase_us": dict(zip(("prep", "logits", "softmax", "grads"),
+                                                         [round(v / 1e3, 2) for v in ph]))}
         if eager is not None:
             a, b = xq.clone().requires_grad_(), xp.clone().requires_grad_()
             tgt = torch.arange(bq, device=dev) * (bp // bq)

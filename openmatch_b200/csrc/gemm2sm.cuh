@@ -181,8 +181,21 @@ struct Gemm2Cfg {
 // SPIN: 0 suspending try_wait, 1 spinning test_wait.  TILE_N: pair tile width.  MASKED: 9-operand MMA form.
 // MODE (rate probes, results are garbage): 1 = MMA only (no TMA, the issuer never waits for operands),
 // 2 = loads only (the issuer waits and commits but issues no MMA).
+// RELAY: the peer's TMA loads complete on a barrier in the peer's OWN shared memory and one relay thread forwards a
+// single arrival per stage to the leader (instead of every complete_tx of the peer's TMA crossing to the leader SM).
+// TRACE (measurement only): pair 0 records %globaltimer per k-block: [rank][role][kb], roles: 0 producer passed the
+// empty wait, 1 producer issued its loads, 2 MMA thread passed the full wait, 3 MMA thread issued the commit,
+// 4 relay saw the local stage land
+__device__ unsigned long long om_2sm_trace[2][5][64];
+__device__ __forceinline__ void trace2(bool on, uint32_t rank, int role, int i) {
+  if (on && i < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    om_2sm_trace[rank][role][i] = t;
+  }
+}
 template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, int SPIN = 0, int TILE_N = 256, bool MASKED = false,
-          int MODE = 0>
+          int MODE = 0, bool RELAY = false, bool TRACE = false>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                      int K, const __grid_constant__ Epi epi) {
@@ -194,7 +207,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty_bar = full_bar + STAGES;                                    // one per CTA (multicast commit)
   uint64_t* tfull_bar = empty_bar + STAGES;                                   // one per CTA (multicast commit)
   uint64_t* tempty_bar = tfull_bar + 2;                                       // used in the leader only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* lfull_bar = tempty_bar + 2;                                       // RELAY: peer-local "my loads landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lfull_bar + STAGES);
   uint8_t* epi_smem = smem + Cfg::kEpiOffset;
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -209,8 +223,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 2);  // one arrive.expect_tx per CTA of the pair
+      // RELAY: the leader's arrive.expect_tx + the relay's arrival; otherwise ONE arrive.expect_tx by the leader that
+      // covers the bytes of both CTAs (the peer only issues its loads: a remote mbarrier arrive with cluster-scope
+      // release stalls the issuing thread for ~0.6 - 0.8 us, measured, which throttled the peer to one stage per that)
+      mbar_init(&full_bar[i], RELAY ? 2 : 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&lfull_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -243,14 +261,20 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int row_b = n_blk * Cfg::kTileN + static_cast<int>(rank) * (Cfg::kTileN / 2);
         for (int kb = 0; kb < num_k; ++kb) {
           wait2<SPIN>(&empty_bar[stage], phase ^ 1u, 1);
+          trace2(TRACE && tile == 0, rank, 0, kb);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          const uint32_t leader_full = mapa_rank(&full_bar[stage], 0);
-          if (rank == 0)
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          else
-            mbar_arrive_expect_tx_cluster(leader_full, Cfg::kStageBytes);
-          tma_load_2d_2sm(sa, &tmA, leader_full, kb * kBlockK, row_a);
-          tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, leader_full, kb * kBlockK, row_b);
+          if constexpr (RELAY) {
+            uint64_t* bar = rank == 0 ? &full_bar[stage] : &lfull_bar[stage];
+            mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
+            tma_load_2d(sa, &tmA, bar, kb * kBlockK, row_a);
+            tma_load_2d(sa + Cfg::kABytes, &tmB, bar, kb * kBlockK, row_b);
+          } else {
+            const uint32_t leader_full = mapa_rank(&full_bar[stage], 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_2sm(sa, &tmA, leader_full, kb * kBlockK, row_a);
+            tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, leader_full, kb * kBlockK, row_b);
+          }
+          trace2(TRACE && tile == 0, rank, 1, kb);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -272,6 +296,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < num_k; ++kb) {
           if constexpr (MODE != 1) wait2<SPIN>(&full_bar[stage], phase, 3);
           tc_fence_after_sync();
+          trace2(TRACE && tile == 0, 0, 2, kb);
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
@@ -288,6 +313,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
           umma_commit_2sm(&empty_bar[stage]);  // frees this stage in both CTAs
+          trace2(TRACE && tile == 0, 0, 3, kb);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -295,6 +321,21 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         umma_commit_2sm(&tfull_bar[as]);  // accumulator complete -> both epilogues
       }
+    }
+  } else if (warp == 3) {
+    if (RELAY && lane == 0 && rank == 1 && MODE != 1) {
+      // ------------------------------ relay (peer only): stage landed here -> one arrival at the leader ----------
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs)
+        for (int kb = 0; kb < num_k; ++kb) {
+          wait2<SPIN>(&lfull_bar[stage], phase, 5);
+          trace2(TRACE && tile == 0, 1, 4, kb);
+          mbar_arrive_cluster(mapa_rank(&full_bar[stage], 0));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
@@ -373,7 +414,7 @@ __global__ void cluster_smid_kernel(unsigned* out) {
 
 // Host launcher (cluster of 2 CTAs along x).  A: [M, K] bf16 row pitch lda; B: [N, K] bf16 row pitch ldb.
 template <int STAGES, bool M_FASTEST, int EPI_WARPS, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0,
-          class Epi>
+          bool RELAY = false, bool TRACE = false, class Epi>
 static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                                        const Epi& epi, int num_sms, cudaStream_t stream, int* pairs_out = nullptr) {
   using Cfg = Gemm2Cfg<STAGES, TILE_N>;
@@ -383,7 +424,7 @@ static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B
     return cudaErrorInvalidValue;
   if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, Cfg::kTileN / 2) != 0)
     return cudaErrorInvalidValue;
-  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN, TILE_N, MASKED, MODE>;
+  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN, TILE_N, MASKED, MODE, RELAY, TRACE>;
   const int smem_bytes = Cfg::kSmemBytes + Epi::smem_bytes(EPI_WARPS);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {

@@ -132,10 +132,10 @@ template <int BN, int STAGES, bool MF, int EW = 4>
 static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters);
 
 // 2-CTA (cta_group::2) core: same exact check
-template <int STAGES, bool MF, int EW, int TILE_N = 256, bool MASKED = false>
+template <int STAGES, bool MF, int EW, int TILE_N = 256, bool MASKED = false, bool RELAY = false>
 static int check_case2(int M, int N, int K, int num_sms) {
-  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d tileN=%d masked=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, TILE_N,
-         (int)MASKED, M, N, K);
+  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d tileN=%d masked=%d relay=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, TILE_N,
+         (int)MASKED, (int)RELAY, M, N, K);
   fflush(stdout);
   std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
   std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
@@ -156,7 +156,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
-  cudaError_t e = launch_gemm2<STAGES, MF, EW, 0, TILE_N, MASKED>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  cudaError_t e = launch_gemm2<STAGES, MF, EW, 0, TILE_N, MASKED, 0, RELAY>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
   if (e != cudaSuccess) {
     printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
     return 1;
@@ -190,7 +190,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   return (bad || fault) ? 1 : 0;
 }
 
-template <int STAGES, bool MF, int EW, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0>
+template <int STAGES, bool MF, int EW, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0, bool RELAY = false>
 static void perf_case2(const char* name, int M, int N, int K, int num_sms, int iters) {
   __nv_bfloat16 *dA, *dB;
   unsigned long long* dcnt;
@@ -211,10 +211,10 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   int pairs = 0;
-  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE, RELAY>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE, RELAY>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -222,9 +222,34 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   ms /= iters;
   unsigned int fault = read_clear_dev_fault();
   double tf = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
-  printf("[perf 2sm spin=%d tileN=%d masked=%d mode=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", SPIN, TILE_N, (int)MASKED, MODE, name, STAGES,
+  printf("[perf 2sm relay=%d spin=%d tileN=%d masked=%d mode=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", (int)RELAY, SPIN, TILE_N, (int)MASKED, MODE, name, STAGES,
          (int)MF, EW, pairs, M, N, K, ms, tf, fault);
   fflush(stdout);
+  cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
+}
+
+template <int MODE, bool RELAY>
+static void trace_case2(int sms) {
+  const int M = 8192, N = 8192, K = 4096;
+  __nv_bfloat16 *dA, *dB;
+  unsigned long long* dcnt;
+  CK(cudaMalloc(&dA, (size_t)M * K * 2));
+  CK(cudaMalloc(&dB, (size_t)N * K * 2));
+  CK(cudaMalloc(&dcnt, 8));
+  CK(cudaMemset(dA, 0, (size_t)M * K * 2));
+  CK(cudaMemset(dB, 0, (size_t)N * K * 2));
+  CK(cudaMemset(dcnt, 0, 8));
+  EpiCount epi{dcnt, 1.0e30f, M, N};
+  for (int i = 0; i < 2; ++i) CK((launch_gemm2<6, false, 8, 0, 256, false, MODE, RELAY, true>(dA, K, dB, K, M, N, K, epi, sms, 0)));
+  CK(cudaDeviceSynchronize());
+  static unsigned long long h[2][5][64];
+  CK(cudaMemcpyFromSymbol(h, om_2sm_trace, sizeof(h)));
+  const unsigned long long t0 = h[0][0][0];
+  printf("[trace 2sm mode=%d relay=%d] ns since the leader's first empty-pass; rows: kb | L.empty L.issued | P.empty P.issued P.landed | full commit\n", MODE, (int)RELAY);
+  for (int kb = 0; kb < 40; ++kb) {
+    auto r = [&](int rank, int role) { return (long long)(h[rank][role][kb] - t0); };
+    printf("  %2d | %6lld %6lld | %6lld %6lld %6lld | %6lld %6lld\n", kb, r(0, 0), r(0, 1), r(1, 0), r(1, 1), RELAY ? r(1, 4) : -1LL, r(0, 2), r(0, 3));
+  }
   cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
 }
 
@@ -233,55 +258,24 @@ static int run_2sm(int sms) {
   fails += check_case2<6, false, 4>(256, 256, 64, sms);     // one pair tile, one k-block
   if (fails) return fails;                                  // nothing else can work
   fails += check_case2<6, false, 8>(300, 520, 192, sms);    // ragged edges, several tiles
-  fails += check_case2<6, false, 8, 128, false>(300, 520, 192, sms);  // 256 x 128 pair tiles
-  fails += check_case2<6, false, 8, 256, true>(300, 520, 192, sms);   // 9-operand MMA form
-  {  // TPC pairing of the clusters
-    unsigned* d_smid;
-    CK(cudaMalloc(&d_smid, 148 * 4));
-    CK(cudaMemset(d_smid, 0xff, 148 * 4));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (sms / 2));
-    cfg.blockDim = dim3(32);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, cluster_smid_kernel, d_smid));
-    CK(cudaDeviceSynchronize());
-    std::vector<unsigned> h(148);
-    CK(cudaMemcpy(h.data(), d_smid, 148 * 4, cudaMemcpyDeviceToHost));
-    int same_tpc = 0, n = sms / 2;
-    for (int c = 0; c < n; ++c) same_tpc += (h[2 * c] / 2 == h[2 * c + 1] / 2) ? 1 : 0;
-    printf("[2sm] clusters whose CTAs sit on SMs 2t, 2t+1: %d of %d; first pairs:", same_tpc, n);
-    for (int c = 0; c < 6; ++c) printf(" (%u,%u)", h[2 * c], h[2 * c + 1]);
-    printf("\n");
-    cudaFree(d_smid);
-  }
+  fails += check_case2<6, false, 8, 128>(300, 520, 192, sms);                // 256 x 128 pair tiles
+  fails += check_case2<6, false, 8, 256, false, true>(300, 520, 192, sms);   // relayed completion
+  fails += check_case2<6, true, 8>(1000, 3000, 768, sms);   // both accumulator buffers, M fastest
+  fails += check_case2<6, false, 4>(256, 256, 512, sms);    // ring wraps
+  trace_case2<0, false>(sms);
   // rate probes (garbage results): the pair-wide MMA alone, the 2-CTA TMA path alone
   perf_case2<6, false, 8, 0, 256, false, 1>("8192^3 MMA only", 8192, 8192, 8192, sms, 5);
   perf_case2<6, false, 8, 0, 256, false, 2>("8192^3 loads only", 8192, 8192, 8192, sms, 5);
-  perf_case2<6, false, 8, 0, 128, false, 1>("8192^3 MMA only", 8192, 8192, 8192, sms, 5);
-  // per-dispatch cost or per-byte cost?  256 x 128 pair tiles halve the FLOP and the peer-smem bytes per MMA
-  perf_case2<6, false, 8, 0, 128, false>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<6, false, 8, 0, 256, true>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<6, false, 8, 0, 128, true>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
-  // one variable at a time: wait flavour (suspending try_wait vs spinning test_wait) x ring depth
-  perf_case2<6, false, 8, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<6, false, 8, 1>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<3, false, 8, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<3, false, 8, 1>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 0, 256, false, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<4, false, 8, 0, 256, false, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 0, 256, false, 0, true>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
   perf_case<256, 4, false, 8>("encoder FFN1 shape (1-CTA)", 32768, 3072, 768, sms, 10);
-  perf_case2<6, false, 8, 1>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
-  perf_case2<6, false, 8, 0>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8, 0, 256, false, 0>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
   perf_case<256, 4, false, 8>("cublas-peak shape 8192^3 (1-CTA)", 8192, 8192, 8192, sms, 5);
-  perf_case2<6, true, 8, 1>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12);
+  perf_case2<6, true, 8, 0, 256, false, 0>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12);
+  perf_case2<6, true, 4, 0, 256, false, 0>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12);
   perf_case<256, 4, true, 8>("search 6980 x 4M sustained (1-CTA)", 6980, 1 << 22, 768, sms, 12);
   fflush(stdout);
-  fails += check_case2<6, false, 4>(256, 256, 512, sms);    // ring wraps
-  fails += check_case2<6, true, 8>(1000, 3000, 768, sms);   // both accumulator buffers, M fastest
   fails += check_case2<6, false, 8>(2048, 2304, 768, sms);  // many tiles per pair
   return fails;
 }
@@ -425,6 +419,13 @@ int main(int argc, char** argv) {
       perf_scan<8, false>("bf16 sustained 4M", 6980, 1 << 22, 768, sms, 12, 42.f, true);
       perf_scan<8, true>("fp16 sustained 4M", 6980, 1 << 22, 768, sms, 12, 42.f, true);
     }
+    return 0;
+  }
+  if (argc > 1 && strcmp(argv[1], "--2smtrace") == 0) {
+    trace_case2<2, true>(sms);
+    trace_case2<0, true>(sms);
+    trace_case2<0, false>(sms);
+    trace_case2<2, false>(sms);
     return 0;
   }
   if (argc > 1 && strcmp(argv[1], "--2sm") == 0) {
