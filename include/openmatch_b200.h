@@ -160,6 +160,7 @@ int om_search_floor_bins(void);
  * "certify" (default 1; 0 = skip the exactness certificate and its escalation: top-k of the fp16 candidate stage),
  * "exact_only" (1 = answer every query with the exact fp32 CUDA-core scan; testing),
  * "debug_stage_scores" (1 = D holds candidate-stage scores instead of fp32 re-scores; error-model measurement),
+ * "pair_scan" (default 1: the scan GEMM runs on CTA pairs, tcgen05 cta_group::2; 0 = single-CTA tiles),
  * "profile" (1 = bracket every kernel launch of a search with CUDA events on the launching stream). */
 int om_index_set_param(om_index* idx, const char* name, int64_t value);
 /* Statistics of the last search: "rounds", "overflow_retries", "candidates" (per query capacity),

@@ -1,25 +1,31 @@
-// EXPERIMENTAL (selftest only, not linked into libopenmatch_b200.so): 2-CTA (tcgen05 cta_group::2) variant of the
-// GEMM core in gemm.cuh:   C[m, n] = sum_k A[m, k] * B[n, k].
-// Measured on B200 (build/selftest_gemm --2sm): bit-exact, but ~770 TFLOP/s on every shape (the single-CTA core:
-// 1 440 - 1 710), independent of ring depth and wait flavour - see DESIGN.md section 7.
+// 2-CTA (tcgen05 cta_group::2) variant of the GEMM core in gemm.cuh:   C[m, n] = sum_k A[m, k] * B[n, k].
 //
-// Idea: the single-CTA 128 x 256 tile moves (128 + 256) x 64 x 2 B of operands into shared memory per
-// 2 x 128 x 256 x 64 FLOP (85 FLOP/B).  Here a CTA PAIR (cluster of 2, the two SMs of a TPC) owns a
-// 256 x 256 tile: CTA r loads A rows [128 r, 128 r + 128) and B rows [128 r, 128 r + 128) of the tile, the
-// leader (rank 0) issues tcgen05.mma.cta_group::2 with M = 256, N = 256, and each SM's tensor core reads the
-// B half it does not hold from its peer's shared memory.  Per SM: 32 KB of operands per 4.2 MFLOP = 128 FLOP/B.
+// The single-CTA 128 x 256 tile moves (128 + 256) x 64 x 2 B = 48 KB of operands into an SM per 4.2 MFLOP, and the
+// SM's ingest path (~64 B/clk) is what bounds that mainloop.  Here a CTA PAIR (cluster of 2 = the two SMs of a TPC)
+// owns a 256 x 256 tile: CTA r loads A rows [128 r, +128) and B rows [128 r, +128) of the tile, the leader (rank 0)
+// issues tcgen05.mma.cta_group::2 with M = 256, N = 256, and each SM's tensor core reads the B half it does not hold
+// from its peer's shared memory.  Per SM: 32 KB of operands per 4.2 MFLOP - the mainloop becomes MMA-bound.
+// Measured (build/selftest_gemm --2sm, profiles/r02_2sm_leadertx.log): 1 711 TFLOP/s on the encoder FFN1 shape
+// (single-CTA core 1 600), 1 614 on 8192^3 (1 373), 1 515 on the sustained search sweep (1 437); bit-exact.
 //
-//   both CTAs, warp 0 lane 0   TMA producer : own A tile + own B half -> own smem ring; the transaction bytes
-//                                             of BOTH CTAs complete on the LEADER's full barrier (.cta_group::2)
+//   both CTAs, warp 0 lane 0   TMA producer : own A tile + own B half -> own smem ring; the transaction bytes of
+//                                             BOTH CTAs complete on the LEADER's full barrier (.cta_group::2), armed
+//                                             by ONE arrive.expect_tx of the leader for the bytes of both.  (A remote
+//                                             mbarrier arrive from the peer - the first version of this file - stalls
+//                                             the issuing thread 0.6 - 0.8 us and throttled the pair to 770 TFLOP/s:
+//                                             profiles/r02_2sm_trace_remote_arrive.log.)
 //   leader,    warp 1 lane 0   MMA issuer   : waits the leader's full barrier, issues the pair-wide MMAs;
 //                                             tcgen05.commit ... multicast frees the smem slot / publishes the
 //                                             accumulator in BOTH CTAs
 //   both CTAs, warp 2          TMEM allocator (cta_group::2: same warp index in both CTAs)
-//   both CTAs, warps 4..       epilogue     : own 128 accumulator rows (TMEM lanes) -> Epi functor; the
-//                                             "accumulator drained" arrivals of both CTAs go to the leader
+//   both CTAs, warps 4..       epilogue     : own 128 accumulator rows (TMEM lanes) -> Epi functor (same contract as
+//                                             gemm.cuh, including multi-pass functors); the "accumulator drained"
+//                                             arrivals of both CTAs go to the leader
 //
-// Static persistent schedule over pairs (tile = pair + i * num_pairs); same Epi functor contract as gemm.cuh
-// (kPasses == 1 functors).
+// Tile schedule: static (tile = pair + i * num_pairs) or dynamic (tile_counter != nullptr): the leader's producer
+// claims pair tiles from a global counter, pushes each claim into the peer's shared memory with one 8-byte remote
+// store (sequence number | tile; the peer's producer polls its own shared memory), and both producers publish the tile
+// to the roles of their CTA through the same 4-deep ring as gemm.cuh.
 #pragma once
 #include <algorithm>
 
@@ -51,13 +57,14 @@ __device__ __forceinline__ uint32_t mapa_rank(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Relaxed: the only user is "accumulator drained" (the tcgen05.ld results are already in registers, ordered by
+// tcgen05.wait::ld + fence::before_thread_sync); a cluster-scope RELEASE arrive stalls the issuing thread for
+// 0.6 - 0.8 us (profiles/r02_2sm_trace_remote_arrive.log).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
-               "r"(bytes)
-               : "memory");
+__device__ __forceinline__ void st_cluster_u64(uint32_t cluster_addr, unsigned long long v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose transaction bytes complete on an mbarrier of the pair's leader
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t leader_bar_cluster_addr,
@@ -78,8 +85,8 @@ __device__ __forceinline__ void tmem_relinquish_2sm() {
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -87,19 +94,6 @@ __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t d_tmem, uint64_t a_des
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// the 9-operand form CUTLASS emits (explicit all-zero disable-output-lane mask)
-__device__ __forceinline__ void umma_bf16_ss_2sm_masked(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                        uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
-      "}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
       : "memory");
 }
 // arrive (count 1) on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so
@@ -111,111 +105,46 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
-// SPIN = 1: poll with mbarrier.test_wait (never suspends the thread) and cluster-scope acquire.  Bring-up switch for
-// the question "does a suspended try_wait wake up promptly when the completing arrival comes from the peer SM?"
-__device__ __forceinline__ bool mbar_test_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-template <int SPIN>
-__device__ __forceinline__ void wait2(uint64_t* bar, uint32_t parity, uint32_t site) {
-  if constexpr (SPIN == 0) {
-    mbar_wait(bar, parity, site);
-  } else {
-    const long long t0 = clock64();
-    uint32_t spins = 0;
-    while (!mbar_test_wait_cluster(bar, parity)) {
-      if ((++spins & 4095u) != 0) continue;
-      if (*reinterpret_cast<volatile unsigned int*>(&om_dev_fault) != 0u) return;
-      if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {
-        atomicCAS(&om_dev_fault, 0u, (site << 16) | (blockIdx.x & 0xffffu) | 0x80000000u);
-        return;
-      }
-    }
-  }
-}
-template <int SPIN>
-__device__ __forceinline__ void wait2_warp(uint64_t* bar, uint32_t parity, uint32_t site) {
-  if constexpr (SPIN == 0) {
-    mbar_wait_warp(bar, parity, site);
-  } else {
-    if ((threadIdx.x & 31u) == 0) {
-      const long long t0 = clock64();
-      uint32_t spins = 0;
-      while (!mbar_test_wait_cluster(bar, parity)) {
-        __nanosleep(32);
-        if ((++spins & 4095u) != 0) continue;
-        if (*reinterpret_cast<volatile unsigned int*>(&om_dev_fault) != 0u) break;
-        if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {
-          atomicCAS(&om_dev_fault, 0u, (site << 16) | (blockIdx.x & 0xffffu) | 0x80000000u);
-          break;
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
-
-template <int STAGES, int TILE_N = 256>
+template <int STAGES>
 struct Gemm2Cfg {
-  static_assert(TILE_N == 256 || TILE_N == 128, "pair tile N: 256 or 128");
-  static constexpr int kTileM = 256, kTileN = TILE_N;       // per CTA pair
+  static constexpr int kTileM = 256, kTileN = 256;            // per CTA pair
   static constexpr int kABytes = kBlockM * kBlockK * 2;       // this CTA's 128 A rows
   static constexpr int kBBytes = (kTileN / 2) * kBlockK * 2;  // this CTA's half of B
   static constexpr int kStageBytes = kABytes + kBBytes;       // 32 KB
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kEpiOffset = kBarOffset + 1024;
   static constexpr int kSmemBytes = kEpiOffset + 1024;
-  static constexpr int kTmemCols = 2 * TILE_N;  // double-buffered accumulator columns per CTA
+  static constexpr int kTmemCols = 2 * kTileN;  // double-buffered accumulator columns per CTA
 };
 
-// SPIN: 0 suspending try_wait, 1 spinning test_wait.  TILE_N: pair tile width.  MASKED: 9-operand MMA form.
-// MODE (rate probes, results are garbage): 1 = MMA only (no TMA, the issuer never waits for operands),
-// 2 = loads only (the issuer waits and commits but issues no MMA).
-// RELAY: the peer's TMA loads complete on a barrier in the peer's OWN shared memory and one relay thread forwards a
-// single arrival per stage to the leader (instead of every complete_tx of the peer's TMA crossing to the leader SM).
-// TRACE (measurement only): pair 0 records %globaltimer per k-block: [rank][role][kb], roles: 0 producer passed the
-// empty wait, 1 producer issued its loads, 2 MMA thread passed the full wait, 3 MMA thread issued the commit,
-// 4 relay saw the local stage land
-__device__ unsigned long long om_2sm_trace[2][5][64];
-__device__ __forceinline__ void trace2(bool on, uint32_t rank, int role, int i) {
-  if (on && i < 64) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    om_2sm_trace[rank][role][i] = t;
-  }
-}
-template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, int SPIN = 0, int TILE_N = 256, bool MASKED = false,
-          int MODE = 0, bool RELAY = false, bool TRACE = false>
+// MODE (rate probes of the selftest, results are garbage): 1 = MMA only (no TMA, the issuer never waits for
+// operands), 2 = loads only (the issuer waits and commits but issues no MMA).  0 in the product.
+template <int STAGES, bool M_FASTEST, int EPI_WARPS, class Epi, bool F16 = false, int MODE = 0>
 __global__ void __launch_bounds__(kGemmProducerThreads + 32 * EPI_WARPS, 1)
-gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                     int K, const __grid_constant__ Epi epi) {
-  using Cfg = Gemm2Cfg<STAGES, TILE_N>;
-  static_assert(Epi::kPasses == 1, "2-CTA core supports single-pass epilogues");
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                const __grid_constant__ Epi epi, int* tile_counter) {
+  using Cfg = Gemm2Cfg<STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);  // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;                                    // one per CTA (multicast commit)
   uint64_t* tfull_bar = empty_bar + STAGES;                                   // one per CTA (multicast commit)
   uint64_t* tempty_bar = tfull_bar + 2;                                       // used in the leader only
-  uint64_t* lfull_bar = tempty_bar + 2;                                       // RELAY: peer-local "my loads landed"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lfull_bar + STAGES);
+  constexpr int kSched = 4, kPush = 8;
+  uint64_t* sfull_bar = tempty_bar + 2;  // tile ring of this CTA: producer -> MMA thread (leader) + epilogue warps
+  uint64_t* sempty_bar = sfull_bar + kSched;
+  volatile unsigned long long* push_ring = reinterpret_cast<volatile unsigned long long*>(sempty_bar + kSched);  // leader -> peer
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(push_ring + kPush);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(tile_ring) + kSched);
   uint8_t* epi_smem = smem + Cfg::kEpiOffset;
+  static_assert((2 * STAGES + 4 + 2 * kSched + kPush) * 8 + kSched * 4 + 8 <= 1024, "barrier block overflows its 1 KB");
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = static_cast<int>(threadIdx.x & 31);
   const uint32_t rank = cluster_ctarank();  // 0 = leader
   const int pair = static_cast<int>(cluster_id_x());
   const int num_pairs = static_cast<int>(cluster_count_x());
+  const bool dyn = tile_counter != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -223,17 +152,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      // RELAY: the leader's arrive.expect_tx + the relay's arrival; otherwise ONE arrive.expect_tx by the leader that
-      // covers the bytes of both CTAs (the peer only issues its loads: a remote mbarrier arrive with cluster-scope
-      // release stalls the issuing thread for ~0.6 - 0.8 us, measured, which throttled the peer to one stage per that)
-      mbar_init(&full_bar[i], RELAY ? 2 : 1);
+      mbar_init(&full_bar[i], 1);  // ONE arrive.expect_tx by the leader covering the bytes of both CTAs
       mbar_init(&empty_bar[i], 1);
-      mbar_init(&lfull_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
     }
+    for (int i = 0; i < kSched; ++i) {
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&sempty_bar[i], (rank == 0 ? 1 : 0) + EPI_WARPS);  // MMA thread (leader) + one lane per epilogue warp
+    }
+    for (int i = 0; i < kPush; ++i) push_ring[i] = 0ull;
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -251,52 +181,95 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_k = (K + kBlockK - 1) / kBlockK;
 
   if (warp == 0) {
-    if (lane == 0 && MODE != 1) {
+    if (lane == 0) {
       // ------------------------------ TMA producer (both CTAs) ------------------------------
-      uint32_t stage = 0, phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
-        const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
-        const int row_a = m_blk * Cfg::kTileM + static_cast<int>(rank) * kBlockM;
-        const int row_b = n_blk * Cfg::kTileN + static_cast<int>(rank) * (Cfg::kTileN / 2);
-        for (int kb = 0; kb < num_k; ++kb) {
-          wait2<SPIN>(&empty_bar[stage], phase ^ 1u, 1);
-          trace2(TRACE && tile == 0, rank, 0, kb);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          if constexpr (RELAY) {
-            uint64_t* bar = rank == 0 ? &full_bar[stage] : &lfull_bar[stage];
-            mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
-            tma_load_2d(sa, &tmA, bar, kb * kBlockK, row_a);
-            tma_load_2d(sa + Cfg::kABytes, &tmB, bar, kb * kBlockK, row_b);
-          } else {
+      uint32_t stage = 0, phase = 0, sslot = 0, sphase = 0;
+      unsigned seq = 1;  // claims so far + 1 (0 = "nothing pushed yet" in the peer's ring)
+      int tile = pair, next = 0;
+      if (dyn && rank == 0) {
+        tile = atomicAdd(tile_counter, 1);
+        if (tile >= num_tiles) tile = -1;
+      }
+      while (true) {
+        if (dyn) {
+          if (rank == 0) {  // push the claim to the peer: one relaxed 8-byte remote store, nobody waits for it here
+            st_cluster_u64(mapa_rank(const_cast<unsigned long long*>(&push_ring[seq % kPush]), 1),
+                           (static_cast<unsigned long long>(seq) << 32) | static_cast<uint32_t>(tile));
+          } else {  // the peer polls its own shared memory for claim number `seq`
+            const long long t0 = clock64();
+            unsigned long long v;
+            while (static_cast<unsigned>((v = push_ring[seq % kPush]) >> 32) != seq) {
+              if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {
+                atomicCAS(&om_dev_fault, 0u, (9u << 16) | (blockIdx.x & 0xffffu) | 0x80000000u);
+                v = 0xffffffffull;  // -1: stop
+                break;
+              }
+            }
+            tile = static_cast<int>(static_cast<uint32_t>(v));
+          }
+          ++seq;
+          // publish (also the -1 sentinel) to the consumer roles of this CTA
+          mbar_wait(&sempty_bar[sslot], sphase ^ 1u, 5);
+          tile_ring[sslot] = tile;
+          mbar_arrive(&sfull_bar[sslot]);
+          if (++sslot == kSched) {
+            sslot = 0;
+            sphase ^= 1u;
+          }
+          if (tile < 0) break;
+          // claim the next tile now; the atomic's round trip overlaps this tile's loads
+          if (rank == 0) next = atomicAdd(tile_counter, 1);
+        } else {
+          if (tile >= num_tiles) break;
+          next = tile + num_pairs;
+        }
+        if constexpr (MODE != 1) {
+          const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
+          const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
+          const int row_a = m_blk * Cfg::kTileM + static_cast<int>(rank) * kBlockM;
+          const int row_b = n_blk * Cfg::kTileN + static_cast<int>(rank) * (Cfg::kTileN / 2);
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
             const uint32_t leader_full = mapa_rank(&full_bar[stage], 0);
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             tma_load_2d_2sm(sa, &tmA, leader_full, kb * kBlockK, row_a);
             tma_load_2d_2sm(sa + Cfg::kABytes, &tmB, leader_full, kb * kBlockK, row_b);
-          }
-          trace2(TRACE && tile == 0, rank, 1, kb);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
+        tile = (dyn && next >= num_tiles) ? -1 : next;
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ------------------------------ MMA issuer (leader only) ------------------------------
-      constexpr uint32_t idesc = umma_idesc_bf16(Cfg::kTileM, Cfg::kTileN);
-      uint32_t stage = 0, phase = 0;
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(Cfg::kTileM, Cfg::kTileN) : umma_idesc_bf16(Cfg::kTileM, Cfg::kTileN);
+      uint32_t stage = 0, phase = 0, sslot = 0, sphase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      for (int tile = pair;; tile += num_pairs, ++it) {
+        if (dyn) {
+          mbar_wait(&sfull_bar[sslot], sphase, 6);
+          const int t = tile_ring[sslot];
+          mbar_arrive(&sempty_bar[sslot]);
+          if (++sslot == kSched) {
+            sslot = 0;
+            sphase ^= 1u;
+          }
+          if (t < 0) break;
+        } else if (tile >= num_tiles) {
+          break;
+        }
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        wait2<SPIN>(&tempty_bar[as], aphase ^ 1u, 2);
+        mbar_wait(&tempty_bar[as], aphase ^ 1u, 2);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * Cfg::kTileN;
         for (int kb = 0; kb < num_k; ++kb) {
-          if constexpr (MODE != 1) wait2<SPIN>(&full_bar[stage], phase, 3);
+          if constexpr (MODE != 1) mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after_sync();
-          trace2(TRACE && tile == 0, 0, 2, kb);
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
@@ -306,14 +279,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if constexpr (MODE == 2) {
               (void)da;
               (void)db;
-            } else if constexpr (MASKED) {
-              umma_bf16_ss_2sm_masked(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             } else {
-              umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit_2sm(&empty_bar[stage]);  // frees this stage in both CTAs
-          trace2(TRACE && tile == 0, 0, 3, kb);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -321,21 +291,6 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         umma_commit_2sm(&tfull_bar[as]);  // accumulator complete -> both epilogues
       }
-    }
-  } else if (warp == 3) {
-    if (RELAY && lane == 0 && rank == 1 && MODE != 1) {
-      // ------------------------------ relay (peer only): stage landed here -> one arrival at the leader ----------
-      uint32_t stage = 0, phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs)
-        for (int kb = 0; kb < num_k; ++kb) {
-          wait2<SPIN>(&lfull_bar[stage], phase, 5);
-          trace2(TRACE && tile == 0, 1, 4, kb);
-          mbar_arrive_cluster(mapa_rank(&full_bar[stage], 0));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
@@ -347,7 +302,22 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     typename Epi::State st;
     if constexpr (Epi::smem_bytes(EPI_WARPS) > 0)
       epi.bind(st, epi_smem, static_cast<int>(threadIdx.x) - kGemmProducerThreads);
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    uint32_t sslot = 0, sphase = 0;
+    const uint32_t leader_tempty0 = mapa_rank(&tempty_bar[0], 0);
+    for (int tile = pair;; tile += num_pairs, ++it) {
+      if (dyn) {
+        mbar_wait_warp(&sfull_bar[sslot], sphase, 7);
+        tile = tile_ring[sslot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sempty_bar[sslot]);
+        if (++sslot == kSched) {
+          sslot = 0;
+          sphase ^= 1u;
+        }
+        if (tile < 0) break;
+      } else if (tile >= num_tiles) {
+        break;
+      }
       const int m_blk = M_FASTEST ? tile % num_m : tile / num_n;
       const int n_blk = M_FASTEST ? tile / num_m : tile % num_n;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -356,30 +326,41 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int col_base = n_blk * Cfg::kTileN;
       epi.begin(st, row, m_blk128, n_blk);
       if constexpr (Epi::kPrefetch) epi.prefetch(st, row, col_base + half * kChunks * 32);
-      wait2_warp<SPIN>(&tfull_bar[as], aphase, 4);
+      mbar_wait_warp(&tfull_bar[as], aphase, 4);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * Cfg::kTileN + (static_cast<uint32_t>(ew * 32) << 16);
-      const int c0 = half * kChunks;
-      auto run = [&](const uint32_t (&rb)[32], int c, bool has_next) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
-        if constexpr (Epi::kPrefetch)
-          epi.chunk(st, row, col_base + c * 32, v, has_next ? col_base + (c + 1) * 32 : -1);
-        else
-          epi.chunk(st, row, col_base + c * 32, v);
-      };
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32b_x32(taddr + c0 * 32, ra);
 #pragma unroll 1
-      for (int c = c0; c + 1 < c0 + kChunks; c += 2) {
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rb);
-        run(ra, c, true);
-        tmem_ld_wait();
-        const bool more = c + 2 < c0 + kChunks;
-        if (more) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
-        run(rb, c + 1, more);
+      for (int pass = 0; pass < Epi::kPasses; ++pass) {
+        if constexpr (Epi::kPasses > 1) {
+          if (pass > 0) {
+            if (!epi.need_pass(st, pass)) break;  // warp-uniform decision
+            epi.between(st, row);
+          }
+        }
+        const int c0 = half * kChunks;
+        auto run = [&](const uint32_t (&rb)[32], int c, bool has_next) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
+          if constexpr (Epi::kPasses > 1)
+            epi.chunk(st, row, col_base + c * 32, v, pass);
+          else if constexpr (Epi::kPrefetch)
+            epi.chunk(st, row, col_base + c * 32, v, has_next ? col_base + (c + 1) * 32 : -1);
+          else
+            epi.chunk(st, row, col_base + c * 32, v);
+        };
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(taddr + c0 * 32, ra);
+#pragma unroll 1
+        for (int c = c0; c + 1 < c0 + kChunks; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rb);
+          run(ra, c, true);
+          tmem_ld_wait();
+          const bool more = c + 2 < c0 + kChunks;
+          if (more) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
+          run(rb, c + 1, more);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -387,7 +368,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (rank == 0)
           mbar_arrive(&tempty_bar[as]);
         else
-          mbar_arrive_cluster(mapa_rank(&tempty_bar[as], 0));
+          mbar_arrive_cluster(leader_tempty0 + as * 8u);
       }
       epi.end(st, row);
     }
@@ -402,29 +383,21 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-// Which SMs host the two CTAs of each cluster?  out[2 * cluster + rank] = %smid.  (cta_group::2 needs the two SMs of
-// one TPC; a cluster of 2 is the only placement control there is.)
-__global__ void cluster_smid_kernel(unsigned* out) {
-  if (threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    out[2 * cluster_id_x() + cluster_ctarank()] = smid;
-  }
-}
-
-// Host launcher (cluster of 2 CTAs along x).  A: [M, K] bf16 row pitch lda; B: [N, K] bf16 row pitch ldb.
-template <int STAGES, bool M_FASTEST, int EPI_WARPS, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0,
-          bool RELAY = false, bool TRACE = false, class Epi>
+// Host launcher (cluster of 2 CTAs along x).  A: [M, K] row pitch lda; B: [N, K] row pitch ldb; 2-byte elements (bf16,
+// or IEEE half with F16).  dynamic_sched: see gemm.cuh.  Returns cudaErrorNotSupported if no cluster of this kernel
+// fits on the device.
+template <int STAGES, bool M_FASTEST, int EPI_WARPS, bool F16 = false, int MODE = 0, class Epi>
 static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
-                                       const Epi& epi, int num_sms, cudaStream_t stream, int* pairs_out = nullptr) {
-  using Cfg = Gemm2Cfg<STAGES, TILE_N>;
+                                       const Epi& epi, int num_sms, cudaStream_t stream, bool dynamic_sched = false,
+                                       int* pairs_out = nullptr) {
+  using Cfg = Gemm2Cfg<STAGES>;
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   CUtensorMap tmA, tmB;
   if (make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBlockK, kBlockM) != 0)
     return cudaErrorInvalidValue;
   if (make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBlockK, Cfg::kTileN / 2) != 0)
     return cudaErrorInvalidValue;
-  auto kern = gemm2_bf16_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, SPIN, TILE_N, MASKED, MODE, RELAY, TRACE>;
+  auto kern = gemm2_tn_kernel<STAGES, M_FASTEST, EPI_WARPS, Epi, F16, MODE>;
   const int smem_bytes = Cfg::kSmemBytes + Epi::smem_bytes(EPI_WARPS);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -445,19 +418,35 @@ static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // The persistent schedule needs every cluster co-resident: a GPC with an odd SM count leaves one SM without a
-  // partner, so fewer than num_sms / 2 pairs fit (a second wave of clusters would double the run time).
+  // partner, so fewer than num_sms / 2 pairs may fit (a second wave of clusters would double the run time).
   static int max_pairs = 0;  // per instantiation
   if (!max_pairs) {
     cfg.gridDim = dim3(2 * (num_sms / 2));
     int n = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
     if (e != cudaSuccess) return e;
-    max_pairs = std::max(1, std::min(n, num_sms / 2));
+    if (n < 1) return cudaErrorNotSupported;
+    max_pairs = std::min(n, num_sms / 2);
   }
   const int pairs = std::max(1, std::min(num_tiles, max_pairs));
   cfg.gridDim = dim3(2 * pairs);
   if (pairs_out) *pairs_out = pairs;
-  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, epi);
+  int* counter = nullptr;
+  if (dynamic_sched) {
+    counter = next_tile_counter(stream);
+    if (!counter) return cudaErrorMemoryAllocation;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, epi, counter);
+}
+
+// Which SMs host the two CTAs of each cluster?  out[2 * cluster + rank] = %smid.  (cta_group::2 needs the two SMs of
+// one TPC; a cluster of 2 is the only placement control there is.)
+__global__ void cluster_smid_kernel(unsigned* out) {
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    out[2 * cluster_id_x() + cluster_ctarank()] = smid;
+  }
 }
 
 }  // namespace om

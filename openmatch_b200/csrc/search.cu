@@ -38,6 +38,7 @@
 
 #include "common.h"
 #include "gemm.cuh"
+#include "gemm2sm.cuh"
 #include "nccl_dyn.h"
 #include "scan_epilogue.cuh"
 
@@ -706,6 +707,7 @@ struct om_index {
   int64_t rescore_slack = -1;
   int force_safe = 0;
   int dynamic_sched = 1;  // claim scan tiles from a global counter (keeps CTAs on neighbouring corpus tiles)
+  int pair_scan = 1;      // scan GEMM on CTA pairs (cta_group::2, gemm2sm.cuh); 0 = the single-CTA core of gemm.cuh
   int growth = 0;         // each round scans (growth - 1) x the rows seen so far; 0 = auto: 2 for query batches (measured
                           // best at nq = 6 980: fewest filter survivors), 8 for <= 256 queries (HBM-bound streaming
                           // regime: 5 instead of 13 dependent scan + select launch pairs over 8.8 M rows)
@@ -868,6 +870,8 @@ int om_index_set_param(om_index* ix, const char* name, int64_t value) {
     ix->growth = static_cast<int>(value);
   } else if (!strcmp(name, "dynamic_sched")) {
     ix->dynamic_sched = value != 0;
+  } else if (!strcmp(name, "pair_scan")) {
+    ix->pair_scan = value != 0;
   } else if (!strcmp(name, "profile")) {
     ix->profile = static_cast<int>(value);
   } else if (!strcmp(name, "certify")) {
@@ -1070,15 +1074,22 @@ int sweep_chunk(om_index* ix, const Level& L, int q0, int nqc, bool safe, int sm
       Timed t(ix, st, 0);
       if (L.mode == 0) {
         const __half* xrows = ix->xh + static_cast<size_t>(pos) * ix->dpad;
-        cudaError_t e;
+        cudaError_t e = cudaErrorNotSupported;
+        const bool dynsched = ix->dynamic_sched != 0;
+        const int ncols = static_cast<int>(step);
+        // CTA pairs own 256 query rows per tile: with <= 128 queries the peer's half would be padding (and the sweep is
+        // HBM-bound there: the single-CTA ring keeps more corpus bytes in flight per SM)
+        const bool pair = ix->pair_scan != 0 && nqc > kBlockM;
         if (first) {
-          EpiScan<true> epi{L.thr, L.cand, L.count, overflow, nqc, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
-          e = launch_gemm<256, 4, true, 8, EpiScan<true>, true>(qh, ix->dpad, xrows, ix->dpad, nqc, static_cast<int>(step),
-                                                                ix->d, epi, sms, st, ix->dynamic_sched != 0);
+          EpiScan<true> epi{L.thr, L.cand, L.count, overflow, nqc, ncols, C, static_cast<uint32_t>(pos)};
+          if (pair) e = launch_gemm2<5, true, 8, true>(qh, ix->dpad, xrows, ix->dpad, nqc, ncols, ix->d, epi, sms, st, dynsched);
+          if (e == cudaErrorNotSupported)  // no CTA pair fits (a device without two free SMs per TPC)
+            e = launch_gemm<256, 4, true, 8, EpiScan<true>, true>(qh, ix->dpad, xrows, ix->dpad, nqc, ncols, ix->d, epi, sms, st, dynsched);
         } else {
-          EpiScan<false> epi{L.thr, L.cand, L.count, overflow, nqc, static_cast<int>(step), C, static_cast<uint32_t>(pos)};
-          e = launch_gemm<256, 4, true, 8, EpiScan<false>, true>(qh, ix->dpad, xrows, ix->dpad, nqc, static_cast<int>(step),
-                                                                 ix->d, epi, sms, st, ix->dynamic_sched != 0);
+          EpiScan<false> epi{L.thr, L.cand, L.count, overflow, nqc, ncols, C, static_cast<uint32_t>(pos)};
+          if (pair) e = launch_gemm2<5, true, 8, true>(qh, ix->dpad, xrows, ix->dpad, nqc, ncols, ix->d, epi, sms, st, dynsched);
+          if (e == cudaErrorNotSupported)
+            e = launch_gemm<256, 4, true, 8, EpiScan<false>, true>(qh, ix->dpad, xrows, ix->dpad, nqc, ncols, ix->d, epi, sms, st, dynsched);
         }
         if (e != cudaSuccess) return fail(OM_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
       } else {

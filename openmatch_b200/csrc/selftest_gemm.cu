@@ -132,10 +132,9 @@ template <int BN, int STAGES, bool MF, int EW = 4>
 static void perf_case(const char* name, int M, int N, int K, int num_sms, int iters);
 
 // 2-CTA (cta_group::2) core: same exact check
-template <int STAGES, bool MF, int EW, int TILE_N = 256, bool MASKED = false, bool RELAY = false>
-static int check_case2(int M, int N, int K, int num_sms) {
-  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d tileN=%d masked=%d relay=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, TILE_N,
-         (int)MASKED, (int)RELAY, M, N, K);
+template <int STAGES, bool MF, int EW>
+static int check_case2(int M, int N, int K, int num_sms, bool dyn = false) {
+  printf("[case 2sm] STAGES=%d M_FASTEST=%d EW=%d dyn=%d  M=%d N=%d K=%d ... ", STAGES, (int)MF, EW, (int)dyn, M, N, K);
   fflush(stdout);
   std::vector<__nv_bfloat16> hA((size_t)M * K), hB((size_t)N * K);
   std::vector<float> fA((size_t)M * K), fB((size_t)N * K);
@@ -156,7 +155,7 @@ static int check_case2(int M, int N, int K, int num_sms) {
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   EpiStoreF32 epi{dC, N, nullptr, nullptr, 0, M, N};
-  cudaError_t e = launch_gemm2<STAGES, MF, EW, 0, TILE_N, MASKED, 0, RELAY>(dA, K, dB, K, M, N, K, epi, num_sms, 0);
+  cudaError_t e = launch_gemm2<STAGES, MF, EW>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn);
   if (e != cudaSuccess) {
     printf("LAUNCH FAILED: %s\n", cudaGetErrorString(e));
     return 1;
@@ -190,8 +189,8 @@ static int check_case2(int M, int N, int K, int num_sms) {
   return (bad || fault) ? 1 : 0;
 }
 
-template <int STAGES, bool MF, int EW, int SPIN = 0, int TILE_N = 256, bool MASKED = false, int MODE = 0, bool RELAY = false>
-static void perf_case2(const char* name, int M, int N, int K, int num_sms, int iters) {
+template <int STAGES, bool MF, int EW, int MODE = 0>
+static void perf_case2(const char* name, int M, int N, int K, int num_sms, int iters, bool dyn = false) {
   __nv_bfloat16 *dA, *dB;
   unsigned long long* dcnt;
   CK(cudaMalloc(&dA, (size_t)M * K * 2));
@@ -211,10 +210,10 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   int pairs = 0;
-  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE, RELAY>(dA, K, dB, K, M, N, K, epi, num_sms, 0, &pairs)));
+  for (int i = 0; i < 2; ++i) CK((launch_gemm2<STAGES, MF, EW, false, MODE>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn, &pairs)));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, SPIN, TILE_N, MASKED, MODE, RELAY>(dA, K, dB, K, M, N, K, epi, num_sms, 0)));
+  for (int i = 0; i < iters; ++i) CK((launch_gemm2<STAGES, MF, EW, false, MODE>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -222,61 +221,50 @@ static void perf_case2(const char* name, int M, int N, int K, int num_sms, int i
   ms /= iters;
   unsigned int fault = read_clear_dev_fault();
   double tf = 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12;
-  printf("[perf 2sm relay=%d spin=%d tileN=%d masked=%d mode=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", (int)RELAY, SPIN, TILE_N, (int)MASKED, MODE, name, STAGES,
-         (int)MF, EW, pairs, M, N, K, ms, tf, fault);
+  printf("[perf 2sm mode=%d dyn=%d] %-28s ST=%d MF=%d EW=%d pairs=%d  M=%d N=%d K=%d : %.3f ms  %.1f TFLOP/s  fault=0x%x\n", MODE,
+         (int)dyn, name, STAGES, (int)MF, EW, pairs, M, N, K, ms, tf, fault);
   fflush(stdout);
   cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
 }
 
-template <int MODE, bool RELAY>
-static void trace_case2(int sms) {
-  const int M = 8192, N = 8192, K = 4096;
-  __nv_bfloat16 *dA, *dB;
-  unsigned long long* dcnt;
-  CK(cudaMalloc(&dA, (size_t)M * K * 2));
-  CK(cudaMalloc(&dB, (size_t)N * K * 2));
-  CK(cudaMalloc(&dcnt, 8));
-  CK(cudaMemset(dA, 0, (size_t)M * K * 2));
-  CK(cudaMemset(dB, 0, (size_t)N * K * 2));
-  CK(cudaMemset(dcnt, 0, 8));
-  EpiCount epi{dcnt, 1.0e30f, M, N};
-  for (int i = 0; i < 2; ++i) CK((launch_gemm2<6, false, 8, 0, 256, false, MODE, RELAY, true>(dA, K, dB, K, M, N, K, epi, sms, 0)));
-  CK(cudaDeviceSynchronize());
-  static unsigned long long h[2][5][64];
-  CK(cudaMemcpyFromSymbol(h, om_2sm_trace, sizeof(h)));
-  const unsigned long long t0 = h[0][0][0];
-  printf("[trace 2sm mode=%d relay=%d] ns since the leader's first empty-pass; rows: kb | L.empty L.issued | P.empty P.issued P.landed | full commit\n", MODE, (int)RELAY);
-  for (int kb = 0; kb < 40; ++kb) {
-    auto r = [&](int rank, int role) { return (long long)(h[rank][role][kb] - t0); };
-    printf("  %2d | %6lld %6lld | %6lld %6lld %6lld | %6lld %6lld\n", kb, r(0, 0), r(0, 1), r(1, 0), r(1, 1), RELAY ? r(1, 4) : -1LL, r(0, 2), r(0, 3));
-  }
-  cudaFree(dA), cudaFree(dB), cudaFree(dcnt);
-}
+template <int EW, bool F16 = false, bool PAIR = false>
+static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value, bool dyn = false,
+                      std::vector<unsigned long long>* keys_out = nullptr);
 
 static int run_2sm(int sms) {
   int fails = 0;
   fails += check_case2<6, false, 4>(256, 256, 64, sms);     // one pair tile, one k-block
   if (fails) return fails;                                  // nothing else can work
   fails += check_case2<6, false, 8>(300, 520, 192, sms);    // ragged edges, several tiles
-  fails += check_case2<6, false, 8, 128>(300, 520, 192, sms);                // 256 x 128 pair tiles
-  fails += check_case2<6, false, 8, 256, false, true>(300, 520, 192, sms);   // relayed completion
   fails += check_case2<6, true, 8>(1000, 3000, 768, sms);   // both accumulator buffers, M fastest
   fails += check_case2<6, false, 4>(256, 256, 512, sms);    // ring wraps
-  trace_case2<0, false>(sms);
+  fails += check_case2<5, true, 8>(3000, 9000, 256, sms, true);   // dynamic pair scheduler
+  fails += check_case2<5, false, 4>(300, 520, 192, sms, true);    // fewer tiles than pairs
+  fails += check_case2<5, true, 8>(2048, 2304, 768, sms, true);
+  // the product's scan epilogue on both cores: identical survivor sets
+  {
+    std::vector<unsigned long long> k1, k2;
+    perf_scan<8, false, false>("scan 1M single-CTA", 6980, 1 << 20, 768, sms, 3, 38.f, true, &k1);
+    perf_scan<8, false, true>("scan 1M pair", 6980, 1 << 20, 768, sms, 3, 38.f, true, &k2);
+    const bool same = k1 == k2;
+    printf("[scan pair vs single] survivor sets %s (%zu words)\n", same ? "IDENTICAL" : "DIFFER", k1.size());
+    fails += same ? 0 : 1;
+  }
   // rate probes (garbage results): the pair-wide MMA alone, the 2-CTA TMA path alone
-  perf_case2<6, false, 8, 0, 256, false, 1>("8192^3 MMA only", 8192, 8192, 8192, sms, 5);
-  perf_case2<6, false, 8, 0, 256, false, 2>("8192^3 loads only", 8192, 8192, 8192, sms, 5);
-  perf_case2<6, false, 8, 0, 256, false, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<4, false, 8, 0, 256, false, 0>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
-  perf_case2<6, false, 8, 0, 256, false, 0, true>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
+  perf_case2<6, false, 8, 1>("8192^3 MMA only", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8, 2>("8192^3 loads only", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8>("encoder FFN1 shape", 32768, 3072, 768, sms, 10);
   perf_case<256, 4, false, 8>("encoder FFN1 shape (1-CTA)", 32768, 3072, 768, sms, 10);
-  perf_case2<6, false, 8, 0, 256, false, 0>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
+  perf_case2<6, false, 8>("cublas-peak shape 8192^3", 8192, 8192, 8192, sms, 5);
   perf_case<256, 4, false, 8>("cublas-peak shape 8192^3 (1-CTA)", 8192, 8192, 8192, sms, 5);
-  perf_case2<6, true, 8, 0, 256, false, 0>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12);
-  perf_case2<6, true, 4, 0, 256, false, 0>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12);
+  perf_case2<5, true, 8>("search 6980 x 4M sustained", 6980, 1 << 22, 768, sms, 12, true);
   perf_case<256, 4, true, 8>("search 6980 x 4M sustained (1-CTA)", 6980, 1 << 22, 768, sms, 12);
+  for (int rep = 0; rep < 2; ++rep) {
+    perf_scan<8, false, true>("scan 4M pair", 6980, 1 << 22, 768, sms, 12, 42.f, true);
+    perf_scan<8, false, false>("scan 4M single-CTA", 6980, 1 << 22, 768, sms, 12, 42.f, true);
+  }
+  perf_scan<8, false, true>("scan 4M pair static", 6980, 1 << 22, 768, sms, 12, 42.f, false);
   fflush(stdout);
-  fails += check_case2<6, false, 8>(2048, 2304, 768, sms);  // many tiles per pair
   return fails;
 }
 
@@ -318,9 +306,16 @@ static void perf_case(const char* name, int M, int N, int K, int num_sms, int it
 }
 
 // the product's scan epilogue on the search shape, thresholds set so that nothing survives
-template <int EW, bool F16 = false>
-static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value, bool dyn = false,
-                      std::vector<unsigned long long>* keys_out = nullptr) {
+template <int EW, bool F16, bool PAIR>
+static void perf_scan(const char* name, int M, int N, int K, int num_sms, int iters, float thr_value, bool dyn,
+                      std::vector<unsigned long long>* keys_out) {
+  if (keys_out) rng_state = 777u;  // survivor sets are compared across calls: same operands every time
+  auto launch = [&](const EpiScan<false, EW * 32>& epi, __nv_bfloat16* dA, __nv_bfloat16* dB) {
+    if constexpr (PAIR)
+      return launch_gemm2<5, true, EW, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn);
+    else
+      return launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn);
+  };
   __nv_bfloat16 *dA, *dB;
   CK(cudaMalloc(&dA, (size_t)M * K * 2));
   CK(cudaMalloc(&dB, (size_t)N * K * 2));
@@ -352,10 +347,10 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 2; ++i) CK((launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
+  for (int i = 0; i < 2; ++i) CK(launch(epi, dA, dB));
   CK(cudaDeviceSynchronize());
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK((launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
+  for (int i = 0; i < iters; ++i) CK(launch(epi, dA, dB));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -371,7 +366,7 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   surv /= (iters + 2);
   if (keys_out) {  // survivors of ONE launch, sorted per query: identical across filter variants by construction
     CK(cudaMemset(count, 0, M * 4));
-    CK((launch_gemm<256, 4, true, EW, EpiScan<false, EW * 32>, F16>(dA, K, dB, K, M, N, K, epi, num_sms, 0, dyn)));
+    CK(launch(epi, dA, dB));
     CK(cudaDeviceSynchronize());
     std::vector<int> c1(M);
     CK(cudaMemcpy(c1.data(), count, M * 4, cudaMemcpyDeviceToHost));
@@ -385,8 +380,8 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
       keys_out->insert(keys_out->end(), row.begin(), row.begin() + n);
     }
   }
-  printf("[perf] %-24s EpiScan EW=%d dyn=%d thr=%g N=%d : %.3f ms %.1f TFLOP/s fault=0x%x ovf=%d survivors/query=%.0f (%.2f per warp-tile)\n",
-         name, EW, (int)dyn, thr_value, N, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf,
+  printf("[perf] %-24s EpiScan pair=%d EW=%d dyn=%d thr=%g N=%d : %.3f ms %.1f TFLOP/s fault=0x%x ovf=%d survivors/query=%.0f (%.2f per warp-tile)\n",
+         name, (int)PAIR, EW, (int)dyn, thr_value, N, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf,
          surv / M, surv / M * 32.0 / (N / 256.0) / (EW / 4));
   if (false) printf("%d %d %d %f", 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
   cudaFree(dA), cudaFree(dB), cudaFree(thr), cudaFree(cand), cudaFree(count), cudaFree(ovf);
@@ -419,13 +414,6 @@ int main(int argc, char** argv) {
       perf_scan<8, false>("bf16 sustained 4M", 6980, 1 << 22, 768, sms, 12, 42.f, true);
       perf_scan<8, true>("fp16 sustained 4M", 6980, 1 << 22, 768, sms, 12, 42.f, true);
     }
-    return 0;
-  }
-  if (argc > 1 && strcmp(argv[1], "--2smtrace") == 0) {
-    trace_case2<2, true>(sms);
-    trace_case2<0, true>(sms);
-    trace_case2<0, false>(sms);
-    trace_case2<2, false>(sms);
     return 0;
   }
   if (argc > 1 && strcmp(argv[1], "--2sm") == 0) {

@@ -452,3 +452,30 @@ def test_more_queries_than_one_chunk(om):
     assert Do.data_ptr() == out[0].data_ptr() and torch.equal(Io, Id) and torch.equal(Do, Dd)
     with pytest.raises(ValueError):
         idx.search_device(torch.from_numpy(q).cuda(), 7, out=(out[0][:5], out[1][:5]))
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(70001, 72, 300, 50), (40000, 768, 129, 1000), (9000, 64, 257, 10),
+                                       (300000, 128, 513, 100)])
+def test_pair_scan_and_single_cta_scan_agree(om, n, d, nq, k):
+    # > 128 queries: the scan GEMM runs on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, dynamic pair scheduler);
+    # "pair_scan" = 0 selects the single-CTA core.  Same candidates, same answer, bit for bit, and equal to the oracle.
+    rng = np.random.default_rng(n + nq)
+    x, q = _int_data(rng, n, d, -5, 5), _int_data(rng, nq, d, -5, 5)
+    D0, I0 = oracle.flat_ip_search(q, x, k)
+    idx = om.FlatIPIndex(d)
+    idx.add(x)
+    for pair in (1, 0, 1):
+        idx.set_param("pair_scan", pair)
+        D, I = idx.search(q, k)
+        np.testing.assert_array_equal(I, I0)
+        np.testing.assert_array_equal(D, D0)
+    # Gaussian data: both cores accumulate the same fp16 products in the same order
+    xg = rng.standard_normal((n, d)).astype(np.float32)
+    qg = rng.standard_normal((nq, d)).astype(np.float32)
+    idx = om.FlatIPIndex(d)
+    idx.add(xg)
+    Dp, Ip = idx.search(qg, k)
+    idx.set_param("pair_scan", 0)
+    Ds, Is = idx.search(qg, k)
+    np.testing.assert_array_equal(Ip, Is)
+    np.testing.assert_array_equal(Dp, Ds)

@@ -20,6 +20,8 @@ for N, nq, k in cases:
     import os
     if os.environ.get("OM_PROFILE"):
         idx.set_param("profile", int(os.environ["OM_PROFILE"]))
+    if os.environ.get("OM_PAIR"):
+        idx.set_param("pair_scan", int(os.environ["OM_PAIR"]))
     if os.environ.get("OM_GROWTH"):
         idx.set_param("round_growth", int(os.environ["OM_GROWTH"]))
     chunks = []
