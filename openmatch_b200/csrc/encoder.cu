@@ -30,6 +30,7 @@
 
 #include "common.h"
 #include "gemm.cuh"
+#include "gemm2sm.cuh"
 
 namespace om {
 
@@ -1559,6 +1560,16 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
   const int rms = bert ? 0 : 1;
   const RowNorm normA{e->stats[0], inv_h, d.ln_eps, rms}, normB{e->stats[1], inv_h, d.ln_eps, rms};
   const RowNorm ident{nullptr, inv_h, d.ln_eps, rms};
+  // wide GEMMs (QKV, FFN1: N >= 2 H, plain bf16 epilogues): CTA pairs (cta_group::2, 256 x 256 tiles: half the operand
+  // bytes per SM and FLOP; 1 700 vs 1 595 TFLOP/s on the FFN1 shape, profiles/r02_2sm_product_core.log), single-CTA
+  // tiles when the device cannot host a pair
+  const bool pair_gemm = getenv("OM_ENCODER_SINGLE_CTA") == nullptr;
+  auto wide_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* W, int M, int N, const auto& epi) -> cudaError_t {
+    cudaError_t err = cudaErrorNotSupported;
+    if (pair_gemm) err = launch_gemm2<5, false, 8>(A, K, W, K, M, N, K, epi, sms, st);
+    if (err == cudaErrorNotSupported) err = launch_gemm<256, 4, false, 8>(A, K, W, K, M, N, K, epi, sms, st);
+    return err;
+  };
   // residual GEMMs (N = H): 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
   // waves of full tiles); 8 epilogue warps = 2 column groups per tile -> (H / BN) * 2 <= kStatParts statistics slots
   auto resid_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* W, EpiResidNorm epi) -> cudaError_t {
@@ -1577,7 +1588,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
     {
       EpiQKV epi{tmQKout, e->qk, e->vt, e->Tld, bert ? w.bqkv_fold : nullptr, T, 2 * I, ap.Tvalid_rows, normA};
       // (192-wide tiles with 12 epilogue warps measured 3 % slower here and on FFN1: r02 tile A/B in profiles/README.md)
-      cudaError_t err = launch_gemm<256, 4, false, 8>(e->xb, H, w.wqkv, H, T, 3 * I, H, epi, sms, st);
+      cudaError_t err = wide_gemm(e->xb, H, w.wqkv, T, 3 * I, epi);
       if (err != cudaSuccess) return fail(OM_ECUDA, "QKV GEMM launch failed: %s", cudaGetErrorString(err));
     }
     if (long_seq)
@@ -1596,10 +1607,10 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
       cudaError_t err;
       if (bert) {
         EpiBiasActBf16<ACT_GELU> epi{tmInter, e->inter, F, w.b1_fold, T, F, normB};
-        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
+        err = wide_gemm(e->xb, H, w.w1, T, F, epi);
       } else {
         EpiBiasActBf16<ACT_RELU> epi{tmInter, e->inter, F, nullptr, T, F, normB};
-        err = launch_gemm<256, 4, false, 8>(e->xb, H, w.w1, H, T, F, H, epi, sms, st);
+        err = wide_gemm(e->xb, H, w.w1, T, F, epi);
       }
       if (err != cudaSuccess) return fail(OM_ECUDA, "FFN1 GEMM launch failed: %s", cudaGetErrorString(err));
     }

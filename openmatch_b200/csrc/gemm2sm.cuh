@@ -439,14 +439,4 @@ static inline cudaError_t launch_gemm2(const void* A, int64_t lda, const void* B
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, epi, counter);
 }
 
-// Which SMs host the two CTAs of each cluster?  out[2 * cluster + rank] = %smid.  (cta_group::2 needs the two SMs of
-// one TPC; a cluster of 2 is the only placement control there is.)
-__global__ void cluster_smid_kernel(unsigned* out) {
-  if (threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    out[2 * cluster_id_x() + cluster_ctarank()] = smid;
-  }
-}
-
 }  // namespace om
