@@ -437,7 +437,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops"] if achieved else None, "traffic": traffic,
                      "traffic_note": traffic_note, "frac_of_burst_peak": achieved / peaks["burst"] if achieved and peaks["burst"] else None,
-                     "kernel": "gemm_bf16_tn_kernel<256,4,1,8,EpiScan,F16> (fused Q*X^T + top-k filter)",
+                     "kernel": "gemm2_tn_kernel<5,1,8,EpiScan,F16> (CTA pairs, cta_group::2; fused Q*X^T + top-k filter)",
                      "note": "2*nq*rows*d FLOPs per sweep / CUDA-event time of the scan launches on the launching "
                              "stream; " + peaks["source"],
                      "phase_ms_per_step": {"scan": phase["scan"], "select": phase["select"], "finalize_rescore": phase["finalize"],
