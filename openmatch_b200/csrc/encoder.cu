@@ -1563,7 +1563,7 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
   // wide GEMMs (QKV, FFN1: N >= 2 H, plain bf16 epilogues): CTA pairs (cta_group::2, 256 x 256 tiles: half the operand
   // bytes per SM and FLOP; 1 700 vs 1 595 TFLOP/s on the FFN1 shape, profiles/r02_2sm_product_core.log), single-CTA
   // tiles when the device cannot host a pair
-  const bool pair_gemm = getenv("OM_ENCODER_SINGLE_CTA") == nullptr;
+  static const bool pair_gemm = getenv("OM_ENCODER_SINGLE_CTA") == nullptr;  // measurement switch, read once
   auto wide_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* W, int M, int N, const auto& epi) -> cudaError_t {
     cudaError_t err = cudaErrorNotSupported;
     if (pair_gemm) err = launch_gemm2<5, false, 8>(A, K, W, K, M, N, K, epi, sms, st);

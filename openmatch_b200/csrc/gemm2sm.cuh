@@ -24,7 +24,7 @@
 //
 // Tile schedule: static (tile = pair + i * num_pairs) or dynamic (tile_counter != nullptr): the leader's producer
 // claims pair tiles from a global counter, pushes each claim into the peer's shared memory with one 8-byte remote
-// store (sequence number | tile; the peer's producer polls its own shared memory), and both producers publish the tile
+// atomic max (sequence number | tile; the peer's producer polls its own shared memory), and both producers publish the tile
 // to the roles of their CTA through the same 4-deep ring as gemm.cuh.
 #pragma once
 #include <algorithm>
@@ -63,8 +63,9 @@ __device__ __forceinline__ uint32_t mapa_rank(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void st_cluster_u64(uint32_t cluster_addr, unsigned long long v) {
-  asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
+// fire-and-forget remote reduction (no result: the issuing thread does not wait for the peer SM)
+__device__ __forceinline__ void red_max_cluster_u64(uint32_t cluster_addr, unsigned long long v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.max.u64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose transaction bytes complete on an mbarrier of the pair's leader
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t leader_bar_cluster_addr,
@@ -172,6 +173,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before_sync();
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  __syncthreads();     // (redundant with the cluster barrier; it is the one compute-sanitizer's racecheck models)
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -192,13 +194,15 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       while (true) {
         if (dyn) {
-          if (rank == 0) {  // push the claim to the peer: one relaxed 8-byte remote store, nobody waits for it here
-            st_cluster_u64(mapa_rank(const_cast<unsigned long long*>(&push_ring[seq % kPush]), 1),
-                           (static_cast<unsigned long long>(seq) << 32) | static_cast<uint32_t>(tile));
-          } else {  // the peer polls its own shared memory for claim number `seq`
+          if (rank == 0) {
+            // push the claim to the peer: one 8-byte remote atomic max (sequence | tile only grows in a slot), nobody
+            // waits for it here
+            red_max_cluster_u64(mapa_rank(const_cast<unsigned long long*>(&push_ring[seq % kPush]), 1),
+                                (static_cast<unsigned long long>(seq) << 32) | static_cast<uint32_t>(tile));
+          } else {  // the peer polls its own shared memory (atomically) for claim number `seq`
             const long long t0 = clock64();
             unsigned long long v;
-            while (static_cast<unsigned>((v = push_ring[seq % kPush]) >> 32) != seq) {
+            while (static_cast<unsigned>((v = atomicMax(const_cast<unsigned long long*>(&push_ring[seq % kPush]), 0ull)) >> 32) != seq) {
               if (clock64() - t0 > OM_WAIT_TIMEOUT_CYCLES) {
                 atomicCAS(&om_dev_fault, 0u, (9u << 16) | (blockIdx.x & 0xffffu) | 0x80000000u);
                 v = 0xffffffffull;  // -1: stop

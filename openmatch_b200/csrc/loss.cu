@@ -581,7 +581,24 @@ struct LossWs {
   int maps_nq = 0, maps_np = 0, maps_d = 0;
 };
 constexpr int kLossBarBytes = 65536, kLossSemSlots = (kLossBarBytes - 256 - 64) / 4;
-static LossWs g_loss_ws;  // grown on demand; one process drives one GPU (see header)
+static LossWs g_loss_ws;
+
+// Measurement switches (read once): OM_LOSS_COPY_INPUTS = always convert / copy the inputs (no in-place TMA reads),
+// OM_LOSS_SPLITK = n overrides the K slices of dQ, OM_LOSS_LOOPED_SOFTMAX = three-pass softmax rows.
+struct LossKnobs {
+  bool copy_inputs, looped_softmax;
+  int splitk;  // 0 = automatic
+  LossKnobs() {
+    copy_inputs = getenv("OM_LOSS_COPY_INPUTS") != nullptr;
+    looped_softmax = getenv("OM_LOSS_LOOPED_SOFTMAX") != nullptr;
+    const char* e = getenv("OM_LOSS_SPLITK");
+    splitk = e ? std::max(1, atoi(e)) : 0;
+  }
+};
+static const LossKnobs& loss_knobs() {
+  static const LossKnobs k;
+  return k;
+}  // grown on demand; one process drives one GPU (see header)
 
 }  // namespace om
 
@@ -603,7 +620,7 @@ extern "C" int om_contrastive_loss_fwd_bwd(const void* Q, const void* P, om_dtyp
   const int dpad = (int)round_up(d, 8), npp = (int)round_up(np, 8);
   // aligned bf16 inputs are read in place by TMA (row pitch = d elements must be a multiple of 16 bytes)
   const bool direct = dtype == OM_BF16 && d % 8 == 0 && ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(P)) & 15) == 0 &&
-                      !getenv("OM_LOSS_COPY_INPUTS");
+                      !loss_knobs().copy_inputs;
   size_t off = 0;
   auto carve = [&](size_t bytes) {
     size_t o = off;
@@ -621,7 +638,7 @@ extern "C" int om_contrastive_loss_fwd_bwd(const void* Q, const void* P, om_dtyp
   if (dQ) {
     const int num_k = (np + kBlockK - 1) / kBlockK;
     int want = std::min(std::min(sms / std::max(1, dq_tiles), num_k / 8), kMaxSplit);
-    if (const char* e = getenv("OM_LOSS_SPLITK")) want = std::max(1, std::min(std::min(atoi(e), num_k), std::min(kMaxSplit, sms / std::max(1, dq_tiles))));
+    if (loss_knobs().splitk) want = std::min(std::min(loss_knobs().splitk, num_k), std::min(kMaxSplit, sms / std::max(1, dq_tiles)));
     if (dq_tiles * 8 > kLossSemSlots) want = 1;
     if (want > 1) {
       const int kper = (num_k + want - 1) / want;
@@ -673,7 +690,7 @@ extern "C" int om_contrastive_loss_fwd_bwd(const void* Q, const void* P, om_dtyp
   a.dq_sem = ws.grid_bar + 64;
   a.ts = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.grid_bar) + kLossBarBytes - 64);
   a.sm_fast = (np % 4 == 0 && np <= kSoftmaxMaxCols && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0 &&
-               !getenv("OM_LOSS_LOOPED_SOFTMAX"))
+               !loss_knobs().looped_softmax)
                   ? 1
                   : 0;
 
