@@ -345,7 +345,7 @@ struct EpiResidNorm {
     s.slot = n_blk * parts + s.group;
     // The residual of the tile this CTA processes NEXT (static schedule: tile + gridDim.x, n fastest) is pulled into L2
     // now, a whole tile ahead: its TMA loads then cost an L2 hit instead of an exposed HBM round trip per chunk.
-    if ((threadIdx.x & 31) == 0) {
+    if (bn > 0 && (threadIdx.x & 31) == 0) {  // bn == 0: CTA-pair schedule, no look-ahead
       const int num_n = (N + bn - 1) / bn, num_m = (M + kBlockM - 1) / kBlockM;
       const int next = m_blk * num_n + n_blk + static_cast<int>(gridDim.x);
       if (next < num_m * num_n) {
@@ -1572,7 +1572,16 @@ int om_encode(om_encoder* e, const int64_t* input_ids, const int64_t* attention_
   };
   // residual GEMMs (N = H): 192-wide tiles divide 768 into 4 (1024 tiles = 6.9 waves of 3/4-size tiles instead of 5.2
   // waves of full tiles); 8 epilogue warps = 2 column groups per tile -> (H / BN) * 2 <= kStatParts statistics slots
+  // CTA pairs: 256-wide tiles with 8 epilogue warps (two column groups) fit next to a 5-stage ring of 32 KB stages
+  // (bert-base 6.59 vs 6.80 ms, bert-large 20.4 vs 21.7 ms per batch of 256: profiles/r02_encoder_pair_resid_probe.log)
   auto resid_gemm = [&](const __nv_bfloat16* A, int K, const __nv_bfloat16* W, EpiResidNorm epi) -> cudaError_t {
+    if (pair_gemm && ((H + 255) / 256) * 2 <= kStatParts) {
+      EpiResidNorm e2 = epi;
+      e2.parts = 2;
+      e2.bn = 0;
+      const cudaError_t err = launch_gemm2<5, false, 8>(A, K, W, K, T, H, K, e2, sms, st);
+      if (err != cudaErrorNotSupported) return err;
+    }
     if (H % 192 == 0) return launch_gemm<192, 4, false, 8>(A, K, W, K, T, H, K, epi, sms, st);
     epi.parts = 1;  // 256-wide tiles: a 4-stage ring leaves room for 4 epilogue warps (one column group)
     return launch_gemm<256, 4, false, 4>(A, K, W, K, T, H, K, epi, sms, st);

@@ -353,6 +353,16 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           else
             epi.chunk(st, row, col_base + c * 32, v);
         };
+        if constexpr (epi_rolled<Epi>::value) {  // heavy functors: one copy of the chunk code (see gemm.cuh)
+          uint32_t ra[32];
+#pragma unroll 1
+          for (int c = c0; c < c0 + kChunks; ++c) {
+            tmem_ld_32x32b_x32(taddr + c * 32, ra);
+            tmem_ld_wait();
+            run(ra, c, c + 1 < c0 + kChunks);
+          }
+          continue;
+        }
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32(taddr + c0 * 32, ra);
 #pragma unroll 1
