@@ -383,7 +383,6 @@ static void perf_scan(const char* name, int M, int N, int K, int num_sms, int it
   printf("[perf] %-24s EpiScan pair=%d EW=%d dyn=%d thr=%g N=%d : %.3f ms %.1f TFLOP/s fault=0x%x ovf=%d survivors/query=%.0f (%.2f per warp-tile)\n",
          name, (int)PAIR, EW, (int)dyn, thr_value, N, ms, 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf,
          surv / M, surv / M * 32.0 / (N / 256.0) / (EW / 4));
-  if (false) printf("%d %d %d %f", 2.0 * M * N * (double)K / (ms * 1e-3) / 1e12, read_clear_dev_fault(), hovf);
   cudaFree(dA), cudaFree(dB), cudaFree(thr), cudaFree(cand), cudaFree(count), cudaFree(ovf);
 }
 
