@@ -424,7 +424,7 @@ def main():
         "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "%s: top-%d over %d x %d fp32 corpus resident in HBM, %d queries per step"
                                % (wl["name"], k, total_rows, d, nq), "corpus_rows": total_rows, "rows_per_gpu": n_local, "dim": d,
-                   "k": k, "nq": nq, "candidate_stage": "fp16 tensor-core scan (fp32 accumulate) + fp32 re-score + exactness "
+                   "k": k, "nq": nq, "candidate_stage": "fp16 tensor-core scan on CTA pairs (tcgen05 cta_group::2, fp32 accumulate) + fp32 re-score + exactness "
                    "certificate (escalation: 4096-wide list, then exact fp32 scan)", "rounds": rounds,
                    "parallelism": ("index row-sharded x%d, om_index_search_sharded: shard-sized candidate lists, ONE packed NCCL "
                                    "all-gather per query chunk (scores | ids | floors | error norms), merge + certificate on "
